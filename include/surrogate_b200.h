@@ -1,0 +1,112 @@
+/* surrogate_b200.h -- C-ABI of the B200 (sm_100a) Kriging / RBF hot path.
+ *
+ * The reference (juri117/surrogate-models) is pure Python with no FFI; its boundary is the duck-typed
+ * surrogate protocol of mylibs/kriging.py, mylibs/rbf.py and mylibs/likeli_optimizer.py.  Each entry
+ * point below names the reference method(s) it replaces (file:line into the reference tree).  The Python
+ * host mirror (surrogate-models_b200/mylibs) binds these symbols with ctypes; INTEGRATION.md shows the
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - all arrays are fp64, row-major, contiguous; "theta" is always LINEAR (the caller applies 10**e, as
+ *     Kriging._calc_likelihood_opti_exp does, mylibs/kriging.py:133-136);
+ *   - functions without the _host suffix take DEVICE pointers and enqueue on `stream` (a cudaStream_t
+ *     passed as void*; NULL = default stream) without synchronising;
+ *   - *_host functions take HOST pointers, copy in, compute, copy out and synchronise before returning;
+ *   - return value: 0 on success, a positive cudaError_t, or a negative SM_E_* argument error.  Numeric
+ *     failure is in-band: +inf likelihood / info != 0 (never an error code), like the reference
+ *     (mylibs/kriging.py:101-110);
+ *   - there is no CPU fallback: every entry point launches sm_100a kernels or fails.
+ */
+#ifndef SURROGATE_B200_H
+#define SURROGATE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SM_E_BADARG (-1)   /* null pointer, n < 1, k < 1 or k > SM_KMAX, ... */
+#define SM_E_TOOBIG (-2)   /* problem exceeds a kernel's staging capacity */
+#define SM_KMAX 16
+
+/* RBF kernel ids (mylibs/rbf.py:105-118 and the name dispatch of RBF.update_param, rbf.py:51-64) */
+#define SM_RBF_LIN 0
+#define SM_RBF_CUBIC 1
+#define SM_RBF_GAUS 2
+#define SM_RBF_MQ 3
+#define SM_RBF_IMQ 4
+
+int sm_b200_version(void);
+const char* sm_b200_error_string(int code);
+/* kernels launched by this library since load (bench.py's gpu_launches) */
+long long sm_b200_launch_count(void);
+/* padded size (multiple of 8) and number of doubles of the packed L^-1 operand tiles for n samples */
+int sm_krig_npad(int n);
+size_t sm_krig_mop_doubles(int n);
+
+/* ---- batched likelihood over the reference's grid ------------------------------------------------
+ * Replaces LikeliOptimizer.generate_grid (mylibs/likeli_optimizer.py:50-87) calling
+ * Kriging._calc_likelihood_opti_exp (mylibs/kriging.py:130-141) once per candidate.
+ * Candidate c in [c_begin, c_begin + c_count) of the T^k * P^k grid, flat index c = ip * T^k + it with
+ * dimension 0 the fastest digit (increase_i, likeli_optimizer.py:89-97).  theta_axis[T] holds LINEAR
+ * theta values (10**linspace(-5, 5, T)), p_axis[P] the exponents p.
+ * nll_out[c_count] (may be NULL); best_val / best_idx: first strict minimum (likeli_optimizer.py:79-81),
+ * best_idx is the GLOBAL flat index, -1 (and +inf) when no candidate is finite. */
+int sm_krig_nll_grid(const double* X, const double* y, int n, int k, const double* theta_axis, int T,
+                     const double* p_axis, int P, int64_t c_begin, int64_t c_count, double* nll_out,
+                     double* best_val, int64_t* best_idx, void* stream);
+int sm_krig_nll_grid_host(const double* X, const double* y, int n, int k, const double* theta_axis, int T,
+                          const double* p_axis, int P, int64_t c_begin, int64_t c_count, double* nll_out,
+                          double* best_val, int64_t* best_idx);
+
+/* ---- batched likelihood over an explicit candidate list -------------------------------------------
+ * Replaces a Python loop of Kriging.update_param(theta_c, p_c) + calc_likelihood()
+ * (mylibs/kriging.py:53-63, 95-116; e.g. examples/kriging_r2.py:91-97).  theta[C][k] linear, p[C][k].
+ * best_idx = idx_base + (row of the first minimum). */
+int sm_krig_nll_batch(const double* X, const double* y, int n, int k, const double* theta, const double* p,
+                      int64_t C, int64_t idx_base, double* nll_out, double* best_val, int64_t* best_idx,
+                      void* stream);
+int sm_krig_nll_batch_host(const double* X, const double* y, int n, int k, const double* theta,
+                           const double* p, int64_t C, int64_t idx_base, double* nll_out, double* best_val,
+                           int64_t* best_idx);
+
+/* ---- single-model fit -------------------------------------------------------------------------------
+ * Replaces Kriging.update_param (mylibs/kriging.py:53-63 = _calc_cormat :66-84 + _calc_mu :86-93) and
+ * calc_likelihood (:95-116).  scalars[4] = {nll, mu, sigma2, info}; info 1 = not numerically SPD.
+ * w[n] = R^-1 (y - 1 mu); b[npad] = L^-1 1; rres[npad] = L^-1 (y - 1 mu); Mop[sm_krig_mop_doubles(n)] =
+ * L^-1 as packed 8x8 operand tiles (consumed by sm_krig_predict for the MSE); R[n*n] optional (NULL). */
+int sm_krig_fit(const double* X, const double* y, int n, int k, const double* theta, const double* p,
+                double* scalars, double* w, double* b, double* rres, double* Mop, double* R, void* stream);
+
+/* ---- prediction ---------------------------------------------------------------------------------------
+ * Replaces Kriging.predict (mylibs/kriging.py:206-220) called per query.  mse_out may be NULL; when given,
+ * the ordinary-Kriging mean-squared error (not in the reference) is returned as well and Mop/b/rres must
+ * come from sm_krig_fit. */
+int sm_krig_predict(const double* X, int n, int k, const double* theta, const double* p, const double* w,
+                    double mu, double sigma2, const double* Mop, const double* b, const double* rres,
+                    const double* Xq, int64_t Nq, double* y_out, double* mse_out, void* stream);
+/* fit at (theta, p) then predict Nq host-resident queries; scalars[4] as in sm_krig_fit */
+int sm_krig_fit_predict_host(const double* X, const double* y, int n, int k, const double* theta,
+                             const double* p, const double* Xq, int64_t Nq, double* y_out, double* mse_out,
+                             double* scalars);
+
+/* ---- RBF --------------------------------------------------------------------------------------------------
+ * sm_rbf_fit replaces RBF._calc_coefficiants (mylibs/rbf.py:67-80): coeff = Phi^-1 y.  *info (device int):
+ * 0 ok, > 0 exactly singular at that pivot (np.linalg.solve would raise LinAlgError).  This call
+ * synchronises the stream once (it reads the SPD test result back).
+ * sm_rbf_predict replaces RBF.predict (mylibs/rbf.py:85-103). */
+int sm_rbf_fit(const double* X, const double* y, int n, int k, int kind, double a, double* coeff, int* info,
+               void* stream);
+int sm_rbf_predict(const double* X, int n, int k, int kind, double a, const double* coeff, const double* Xq,
+                   int64_t Nq, double* y_out, void* stream);
+int sm_rbf_fit_host(const double* X, const double* y, int n, int k, int kind, double a, double* coeff,
+                    int* info);
+int sm_rbf_predict_host(const double* X, int n, int k, int kind, double a, const double* coeff,
+                        const double* Xq, int64_t Nq, double* y_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SURROGATE_B200_H */

@@ -1,0 +1,296 @@
+// extern "C" boundary (include/surrogate_b200.h): argument checks, table set-up, kernel launches and the
+// host-buffer wrappers.  No torch types, no CPU arithmetic.
+#include <atomic>
+#include <vector>
+
+#include "../../include/surrogate_b200.h"
+#include "kernels.h"
+
+using namespace smb;
+
+static std::atomic<long long> g_launches{0};
+
+#define SM_TRY(expr)                           \
+    do {                                       \
+        cudaError_t _e = (expr);               \
+        if (_e != cudaSuccess) return (int)_e; \
+    } while (0)
+
+namespace {
+struct Launches {  // accumulates into the global counter on scope exit
+    long long n = 0;
+    ~Launches() { g_launches += n; }
+};
+// stream-ordered device buffer, freed on scope exit
+struct DevBuf {
+    void* p = nullptr;
+    cudaStream_t st;
+    explicit DevBuf(cudaStream_t s) : st(s) {}
+    cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 8, st); }
+    ~DevBuf() { if (p) cudaFreeAsync(p, st); }
+    template <class T> T* as() { return static_cast<T*>(p); }
+};
+bool bad_nk(int n, int k) { return n < 1 || k < 1 || k > SM_KMAX; }
+}  // namespace
+
+namespace {
+struct HostCall {  // one private stream per call; everything is stream ordered and freed at the end
+    cudaStream_t st = nullptr;
+    std::vector<void*> bufs;
+    cudaError_t init() { return cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking); }
+    template <class T> cudaError_t up(const T* h, size_t count, T** d) {
+        void* p = nullptr;
+        cudaError_t e = cudaMallocAsync(&p, count * sizeof(T) ? count * sizeof(T) : 8, st);
+        if (e != cudaSuccess) return e;
+        bufs.push_back(p);
+        *d = static_cast<T*>(p);
+        if (h && count) return cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, st);
+        return cudaSuccess;
+    }
+    template <class T> cudaError_t down(T* h, const T* d, size_t count) {
+        return count ? cudaMemcpyAsync(h, d, count * sizeof(T), cudaMemcpyDeviceToHost, st) : cudaSuccess;
+    }
+    ~HostCall() {
+        for (void* p : bufs) cudaFreeAsync(p, st);
+        if (st) {
+            cudaStreamSynchronize(st);
+            cudaStreamDestroy(st);
+        }
+    }
+};
+}  // namespace
+
+extern "C" {
+
+int sm_b200_version(void) { return 100; }
+long long sm_b200_launch_count(void) { return g_launches.load(); }
+const char* sm_b200_error_string(int code) {
+    if (code == 0) return "ok";
+    if (code == SM_E_BADARG) return "surrogate_b200: bad argument";
+    if (code == SM_E_TOOBIG) return "surrogate_b200: problem exceeds kernel capacity";
+    return cudaGetErrorString((cudaError_t)code);
+}
+int sm_krig_npad(int n) { return (n + 7) / 8 * 8; }
+size_t sm_krig_mop_doubles(int n) {
+    const size_t NT = (size_t)(n + 7) / 8;
+    return NT * (NT + 1) / 2 * 64;
+}
+
+int sm_krig_nll_grid(const double* X, const double* y, int n, int k, const double* theta_axis, int T,
+                     const double* p_axis, int P, int64_t c_begin, int64_t c_count, double* nll_out,
+                     double* best_val, int64_t* best_idx, void* stream) {
+    if (!X || !y || !theta_axis || !p_axis || bad_nk(n, k) || T < 1 || P < 1 || c_begin < 0 || c_count < 0)
+        return SM_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    Launches L;
+    const int npad = sm_krig_npad(n);
+    DevBuf dtab(st), nll_tmp(st);
+    SM_TRY(dtab.alloc((size_t)npad * npad * k * P * 8));
+    SM_TRY(launch_dtab(X, n, k, npad, p_axis, P, dtab.as<double>(), st));
+    L.n += 1;
+    if (!nll_out) {
+        SM_TRY(nll_tmp.alloc((size_t)c_count * 8));
+        nll_out = nll_tmp.as<double>();
+    }
+    NllArgs a{};
+    a.X = X; a.y = y; a.n = n; a.k = k; a.npad = npad;
+    a.C = c_count; a.c_begin = c_begin;
+    a.theta_axis = theta_axis; a.T = T; a.P = P; a.dtab = dtab.as<double>();
+    a.nll_out = nll_out;
+    SM_TRY(launch_nll(a, 0, st, &L.n));
+    if (best_val && best_idx) {
+        SM_TRY(launch_argmin(nll_out, c_count, c_begin, best_val, (long long*)best_idx, st));
+        L.n += 2;
+    }
+    return 0;
+}
+
+int sm_krig_nll_batch(const double* X, const double* y, int n, int k, const double* theta, const double* p,
+                      int64_t C, int64_t idx_base, double* nll_out, double* best_val, int64_t* best_idx,
+                      void* stream) {
+    if (!X || !y || !theta || !p || bad_nk(n, k) || C < 0) return SM_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    Launches L;
+    const int npad = sm_krig_npad(n);
+    DevBuf lg(st), nll_tmp(st);
+    SM_TRY(lg.alloc((size_t)npad * npad * k * 8));
+    SM_TRY(launch_logtab(X, n, k, npad, lg.as<double>(), st));
+    L.n += 1;
+    if (!nll_out) {
+        SM_TRY(nll_tmp.alloc((size_t)C * 8));
+        nll_out = nll_tmp.as<double>();
+    }
+    NllArgs a{};
+    a.X = X; a.y = y; a.n = n; a.k = k; a.npad = npad;
+    a.C = C; a.c_begin = idx_base;
+    a.theta = theta; a.p = p; a.logtab = lg.as<double>();
+    a.nll_out = nll_out;
+    SM_TRY(launch_nll(a, 1, st, &L.n));
+    if (best_val && best_idx) {
+        SM_TRY(launch_argmin(nll_out, C, idx_base, best_val, (long long*)best_idx, st));
+        L.n += 2;
+    }
+    return 0;
+}
+
+int sm_krig_fit(const double* X, const double* y, int n, int k, const double* theta, const double* p,
+                double* scalars, double* w, double* b, double* rres, double* Mop, double* R, void* stream) {
+    if (!X || !y || !theta || !p || !scalars || !w || !b || !rres || !Mop || bad_nk(n, k)) return SM_E_BADARG;
+    Launches L;
+    FitOut out{scalars, w, b, rres, Mop, R};
+    SM_TRY(launch_krig_fit(X, y, n, k, theta, p, out, (cudaStream_t)stream, &L.n));
+    return 0;
+}
+
+int sm_krig_predict(const double* X, int n, int k, const double* theta, const double* p, const double* w,
+                    double mu, double sigma2, const double* Mop, const double* b, const double* rres,
+                    const double* Xq, int64_t Nq, double* y_out, double* mse_out, void* stream) {
+    if (!X || !theta || !p || !w || !Xq || !y_out || bad_nk(n, k) || Nq < 0) return SM_E_BADARG;
+    if (mse_out && (!Mop || !b || !rres)) return SM_E_BADARG;
+    Launches L;
+    PredictArgs a{};
+    a.X = X; a.n = n; a.k = k; a.npad = sm_krig_npad(n);
+    a.theta = theta; a.p = p; a.w = w; a.mu = mu; a.sigma2 = sigma2;
+    a.Mop = Mop; a.b = b; a.rres = rres; a.Xq = Xq; a.Nq = Nq; a.y_out = y_out; a.mse_out = mse_out;
+    cudaError_t e = launch_krig_predict(a, (cudaStream_t)stream, &L.n);
+    if (e == cudaErrorInvalidValue) return SM_E_TOOBIG;
+    return (int)e;
+}
+
+int sm_rbf_fit(const double* X, const double* y, int n, int k, int kind, double a, double* coeff, int* info,
+               void* stream) {
+    if (!X || !y || !coeff || !info || bad_nk(n, k) || kind < 0 || kind > 4) return SM_E_BADARG;
+    Launches L;
+    SM_TRY(launch_rbf_fit(X, y, n, k, kind, a, coeff, info, (cudaStream_t)stream, &L.n));
+    return 0;
+}
+
+int sm_rbf_predict(const double* X, int n, int k, int kind, double a, const double* coeff, const double* Xq,
+                   int64_t Nq, double* y_out, void* stream) {
+    if (!X || !coeff || !Xq || !y_out || bad_nk(n, k) || kind < 0 || kind > 4 || Nq < 0) return SM_E_BADARG;
+    Launches L;
+    SM_TRY(launch_rbf_predict(X, n, k, kind, a, coeff, Xq, Nq, y_out, (cudaStream_t)stream, &L.n));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ host wrappers
+
+int sm_krig_nll_grid_host(const double* X, const double* y, int n, int k, const double* theta_axis, int T,
+                          const double* p_axis, int P, int64_t c_begin, int64_t c_count, double* nll_out,
+                          double* best_val, int64_t* best_idx) {
+    if (!X || !y || !theta_axis || !p_axis || bad_nk(n, k) || T < 1 || P < 1 || c_count < 0) return SM_E_BADARG;
+    HostCall hc;
+    SM_TRY(hc.init());
+    double *dX, *dy, *dth, *dp, *dnll, *dbv;
+    long long* dbi;
+    SM_TRY(hc.up(X, (size_t)n * k, &dX));
+    SM_TRY(hc.up(y, (size_t)n, &dy));
+    SM_TRY(hc.up(theta_axis, (size_t)T, &dth));
+    SM_TRY(hc.up(p_axis, (size_t)P, &dp));
+    SM_TRY(hc.up((const double*)nullptr, (size_t)c_count, &dnll));
+    SM_TRY(hc.up((const double*)nullptr, 1, &dbv));
+    SM_TRY(hc.up((const long long*)nullptr, 1, &dbi));
+    int rc = sm_krig_nll_grid(dX, dy, n, k, dth, T, dp, P, c_begin, c_count, dnll, dbv, (int64_t*)dbi, hc.st);
+    if (rc) return rc;
+    if (nll_out) SM_TRY(hc.down(nll_out, dnll, (size_t)c_count));
+    if (best_val) SM_TRY(hc.down(best_val, dbv, 1));
+    if (best_idx) SM_TRY(hc.down((long long*)best_idx, dbi, 1));
+    SM_TRY(cudaStreamSynchronize(hc.st));
+    return 0;
+}
+
+int sm_krig_nll_batch_host(const double* X, const double* y, int n, int k, const double* theta,
+                           const double* p, int64_t C, int64_t idx_base, double* nll_out, double* best_val,
+                           int64_t* best_idx) {
+    if (!X || !y || !theta || !p || bad_nk(n, k) || C < 0) return SM_E_BADARG;
+    HostCall hc;
+    SM_TRY(hc.init());
+    double *dX, *dy, *dth, *dp, *dnll, *dbv;
+    long long* dbi;
+    SM_TRY(hc.up(X, (size_t)n * k, &dX));
+    SM_TRY(hc.up(y, (size_t)n, &dy));
+    SM_TRY(hc.up(theta, (size_t)C * k, &dth));
+    SM_TRY(hc.up(p, (size_t)C * k, &dp));
+    SM_TRY(hc.up((const double*)nullptr, (size_t)C, &dnll));
+    SM_TRY(hc.up((const double*)nullptr, 1, &dbv));
+    SM_TRY(hc.up((const long long*)nullptr, 1, &dbi));
+    int rc = sm_krig_nll_batch(dX, dy, n, k, dth, dp, C, idx_base, dnll, dbv, (int64_t*)dbi, hc.st);
+    if (rc) return rc;
+    if (nll_out) SM_TRY(hc.down(nll_out, dnll, (size_t)C));
+    if (best_val) SM_TRY(hc.down(best_val, dbv, 1));
+    if (best_idx) SM_TRY(hc.down((long long*)best_idx, dbi, 1));
+    SM_TRY(cudaStreamSynchronize(hc.st));
+    return 0;
+}
+
+int sm_krig_fit_predict_host(const double* X, const double* y, int n, int k, const double* theta,
+                             const double* p, const double* Xq, int64_t Nq, double* y_out, double* mse_out,
+                             double* scalars) {
+    if (!X || !y || !theta || !p || !Xq || !y_out || bad_nk(n, k) || Nq < 0) return SM_E_BADARG;
+    HostCall hc;
+    SM_TRY(hc.init());
+    const int npad = sm_krig_npad(n);
+    double *dX, *dy, *dth, *dp, *dsc, *dw, *db, *dr, *dM, *dXq, *dyo, *dmo = nullptr;
+    SM_TRY(hc.up(X, (size_t)n * k, &dX));
+    SM_TRY(hc.up(y, (size_t)n, &dy));
+    SM_TRY(hc.up(theta, (size_t)k, &dth));
+    SM_TRY(hc.up(p, (size_t)k, &dp));
+    SM_TRY(hc.up((const double*)nullptr, 4, &dsc));
+    SM_TRY(hc.up((const double*)nullptr, (size_t)n, &dw));
+    SM_TRY(hc.up((const double*)nullptr, (size_t)npad, &db));
+    SM_TRY(hc.up((const double*)nullptr, (size_t)npad, &dr));
+    SM_TRY(hc.up((const double*)nullptr, sm_krig_mop_doubles(n), &dM));
+    SM_TRY(hc.up(Xq, (size_t)Nq * k, &dXq));
+    SM_TRY(hc.up((const double*)nullptr, (size_t)Nq, &dyo));
+    if (mse_out) SM_TRY(hc.up((const double*)nullptr, (size_t)Nq, &dmo));
+    int rc = sm_krig_fit(dX, dy, n, k, dth, dp, dsc, dw, db, dr, dM, nullptr, hc.st);
+    if (rc) return rc;
+    double sc[4];
+    SM_TRY(hc.down(sc, dsc, 4));
+    SM_TRY(cudaStreamSynchronize(hc.st));
+    if (scalars) for (int i = 0; i < 4; ++i) scalars[i] = sc[i];
+    if (sc[3] != 0.0) return 0;  // not SPD: in-band (info), nothing to predict with
+    rc = sm_krig_predict(dX, n, k, dth, dp, dw, sc[1], sc[2], dM, db, dr, dXq, Nq, dyo, dmo, hc.st);
+    if (rc) return rc;
+    SM_TRY(hc.down(y_out, dyo, (size_t)Nq));
+    if (mse_out) SM_TRY(hc.down(mse_out, dmo, (size_t)Nq));
+    SM_TRY(cudaStreamSynchronize(hc.st));
+    return 0;
+}
+
+int sm_rbf_fit_host(const double* X, const double* y, int n, int k, int kind, double a, double* coeff, int* info) {
+    if (!X || !y || !coeff || !info || bad_nk(n, k)) return SM_E_BADARG;
+    HostCall hc;
+    SM_TRY(hc.init());
+    double *dX, *dy, *dc;
+    int* di;
+    SM_TRY(hc.up(X, (size_t)n * k, &dX));
+    SM_TRY(hc.up(y, (size_t)n, &dy));
+    SM_TRY(hc.up((const double*)nullptr, (size_t)n, &dc));
+    SM_TRY(hc.up((const int*)nullptr, 1, &di));
+    int rc = sm_rbf_fit(dX, dy, n, k, kind, a, dc, di, hc.st);
+    if (rc) return rc;
+    SM_TRY(hc.down(coeff, dc, (size_t)n));
+    SM_TRY(hc.down(info, di, 1));
+    SM_TRY(cudaStreamSynchronize(hc.st));
+    return 0;
+}
+
+int sm_rbf_predict_host(const double* X, int n, int k, int kind, double a, const double* coeff,
+                        const double* Xq, int64_t Nq, double* y_out) {
+    if (!X || !coeff || !Xq || !y_out || bad_nk(n, k) || Nq < 0) return SM_E_BADARG;
+    HostCall hc;
+    SM_TRY(hc.init());
+    double *dX, *dc, *dXq, *dyo;
+    SM_TRY(hc.up(X, (size_t)n * k, &dX));
+    SM_TRY(hc.up(coeff, (size_t)n, &dc));
+    SM_TRY(hc.up(Xq, (size_t)Nq * k, &dXq));
+    SM_TRY(hc.up((const double*)nullptr, (size_t)Nq, &dyo));
+    int rc = sm_rbf_predict(dX, n, k, kind, a, dc, dXq, Nq, dyo, hc.st);
+    if (rc) return rc;
+    SM_TRY(hc.down(y_out, dyo, (size_t)Nq));
+    SM_TRY(cudaStreamSynchronize(hc.st));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+// Internal declarations shared by the .cu translation units (the public C-ABI is include/surrogate_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+namespace smb {
+
+struct NllArgs {
+    // samples
+    const double* X;  // [n][k] row-major
+    const double* y;  // [n]
+    int n, k, npad;
+    // candidates
+    long long C;        // candidates in this launch
+    long long c_begin;  // global flat index of candidate 0 (grid mode; also offsets argmin indices)
+    // grid mode (MODE 0): theta_axis holds LINEAR theta values (10**exponent done by the caller)
+    const double* theta_axis;
+    int T, P;
+    const double* dtab;  // [k][P][npad][npad]
+    // list mode (MODE 1)
+    const double* theta;  // [C][k] linear
+    const double* p;      // [C][k]
+    const double* logtab;  // [k][npad][npad]
+    // output / scratch
+    double* nll_out;    // [C]
+    double* workspace;  // tile storage for the global-memory variant
+};
+
+struct NllPlan {
+    int variant;  // 0: warp per candidate (smem), 1: CTA per candidate (smem), 2: CTA per candidate (global)
+    int npad, threads, ctas_per_sm, cands_per_cta;
+    size_t smem, tile_bytes;
+};
+
+int sm_count();
+size_t smem_optin();
+NllPlan plan_nll(int n);
+size_t nll_smem_bytes(int npad, int slots, int nwarps, size_t tile_bytes);
+cudaError_t launch_nll(NllArgs a, int mode, cudaStream_t st, long long* launches);
+cudaError_t launch_dtab(const double* X, int n, int k, int npad, const double* p_axis, int P, double* D, cudaStream_t st);
+cudaError_t launch_logtab(const double* X, int n, int k, int npad, double* LG, cudaStream_t st);
+cudaError_t launch_argmin(const double* v, long long C, long long c_begin, double* best_val, long long* best_idx,
+                          cudaStream_t st);
+
+// ---- single-model fit (krig_fit.cu)
+struct FitOut {
+    double* scalars;  // [4] nll, mu, sigma2, info (0 ok / 1 not SPD)
+    double* w;        // [n]   R^-1 (y - 1 mu)
+    double* b;        // [npad] L^-1 1   (zero padded)
+    double* rres;     // [npad] L^-1 (y - 1 mu) (zero padded)
+    double* Mop;      // [NT(NT+1)/2][64] M = L^-1, lower tiles in operand order (A operand of the MSE product)
+    double* R;        // optional [n][n] correlation matrix (may be null)
+};
+size_t fit_tile_doubles(int n);
+cudaError_t launch_krig_fit(const double* X, const double* y, int n, int k, const double* theta, const double* p,
+                            FitOut out, cudaStream_t st, long long* launches);
+
+// ---- prediction (krig_predict.cu)
+struct PredictArgs {
+    const double* X;  // [n][k]
+    int n, k, npad;
+    const double* theta;  // [k]
+    const double* p;      // [k]
+    const double* w;      // [n]
+    double mu, sigma2;
+    const double* Mop;   // M = L^-1 tiles (see FitOut), used when mse_out != null
+    const double* b;     // [npad]
+    const double* rres;  // [npad]
+    const double* Xq;    // [Nq][k]
+    long long Nq;
+    double* y_out;    // [Nq]
+    double* mse_out;  // [Nq] or null
+};
+cudaError_t launch_krig_predict(const PredictArgs& a, cudaStream_t st, long long* launches);
+
+// ---- RBF (rbf.cu)
+cudaError_t launch_rbf_fit(const double* X, const double* y, int n, int k, int kind, double a, double* coeff,
+                           int* info, cudaStream_t st, long long* launches);
+cudaError_t launch_rbf_predict(const double* X, int n, int k, int kind, double a, const double* coeff,
+                               const double* Xq, long long Nq, double* y_out, cudaStream_t st, long long* launches);
+
+}  // namespace smb

@@ -1,0 +1,165 @@
+// Single-model fit: the state Kriging.update_param leaves behind (mylibs/kriging.py:53-63: _calc_cormat
+// :66-84 + _calc_mu :86-93) plus the likelihood of calc_likelihood (:95-116), in Cholesky form, and the
+// quantities prediction needs (:206-220):
+//   R = L L^T ;  a = L^-1 y ;  b = L^-1 1 ;  mu = a.b / b.b ;  rres = a - mu b ;  sigma^2 = |rres|^2 / n
+//   M = L^-1 (tile-packed, operand order)  ;  w = R^-1 (y - 1 mu) = M^T rres
+// One CTA (8 warps) runs the tile engine with right-hand sides [y 1 | I]: the identity block yields
+// L^-T row by row (TRI skipping of its structural zeros).
+#include "tile_chol.cuh"
+#include "kernels.h"
+
+namespace smb {
+
+struct DirectEntry {  // R_ij straight from the coordinates, pow() per entry (one model only)
+    const double* X;
+    const double* th;
+    const double* pw;
+    int k, n;
+    __device__ __forceinline__ double one(int i, int j) const {
+        if (i >= n || j >= n) return (i == j) ? 1.0 : 0.0;
+        double s = 0.0;
+        for (int d = 0; d < k; ++d) {
+            const double dx = fabs(X[(size_t)i * k + d] - X[(size_t)j * k + d]);
+            s = __dadd_rn(s, __dmul_rn(th[d], pow(dx, pw[d])));
+        }
+        return exp(-s);
+    }
+    __device__ __forceinline__ void operator()(int i, int j, double& v0, double& v1) const {
+        v0 = one(i, j);
+        v1 = one(i, j + 1);
+    }
+};
+
+struct FitRhs {  // rows 0/1 of block 0: y^T, 1^T ; block 1+m/8 row m%8: e_m^T
+    const double* y;
+    int n;
+    __device__ __forceinline__ void operator()(int rr, int j, double& v0, double& v1) const {
+        v0 = 0.0;
+        v1 = 0.0;
+        if (rr == 0) {
+            if (j < n) v0 = y[j];
+            if (j + 1 < n) v1 = y[j + 1];
+        } else if (rr == 1) {
+            if (j < n) v0 = 1.0;
+            if (j + 1 < n) v1 = 1.0;
+        } else if (rr >= 8) {
+            const int m = rr - 8;
+            if (j == m) v0 = 1.0;
+            if (j + 1 == m) v1 = 1.0;
+        }
+    }
+};
+
+size_t fit_tile_doubles(int n) {
+    const int NT = (n + 7) / 8;
+    return chol_tiles(NT, NT + 1) * 64;
+}
+
+// Mop layout: tile (Rt, K), K <= Rt, at (Rt (Rt+1)/2 + K) * 64, operand order, element (r, c) = M[8Rt+r][8K+c]
+__global__ void __launch_bounds__(256) krig_fit_kernel(const double* __restrict__ X, const double* __restrict__ y,
+                                                       int n, int k, const double* __restrict__ theta,
+                                                       const double* __restrict__ p, double* __restrict__ tiles,
+                                                       FitOut out) {
+    __shared__ double wscr[8 * 64];
+    __shared__ double th_s[KMAX], p_s[KMAX];
+    __shared__ double sc[2];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int NT = (n + 7) / 8, npad = NT * 8;
+    if (threadIdx.x < k) {
+        th_s[threadIdx.x] = theta[threadIdx.x];
+        p_s[threadIdx.x] = p[threadIdx.x];
+    }
+    __syncthreads();
+    const DirectEntry e{X, th_s, p_s, k, n};
+    const FitRhs rhs{y, n};
+    const CholResult res = tile_cholesky<8, 4, true>(tiles, NT, NT + 1, e, rhs, wscr + wid * 64, wid, lane);
+    const double* rhs_base = tiles + (size_t)NT * (NT + 1) / 2 * 64;
+    if (!res.ok) {
+        if (threadIdx.x == 0) {
+            out.scalars[0] = INFINITY;
+            out.scalars[1] = NAN;
+            out.scalars[2] = NAN;
+            out.scalars[3] = 1.0;
+        }
+        return;
+    }
+    if (wid == 0) {
+        double mu, s2;
+        const double nll = nll_epilogue(rhs_base, n, lane, res.logdet_half, &mu, &s2);
+        if (lane == 0) {
+            out.scalars[0] = nll;
+            out.scalars[1] = mu;
+            out.scalars[2] = s2;
+            out.scalars[3] = 0.0;
+            sc[0] = mu;
+        }
+    }
+    __syncthreads();
+    const double mu = sc[0];
+    for (int j = threadIdx.x; j < npad; j += blockDim.x) {
+        const double* t = rhs_base + (size_t)(j >> 3) * 64;
+        const double a = (j < n) ? t[tile_pos(0, j & 7)] : 0.0, b = (j < n) ? t[tile_pos(1, j & 7)] : 0.0;
+        out.b[j] = b;
+        out.rres[j] = fma(-mu, b, a);
+    }
+    __syncthreads();
+    // w_m = sum_{j >= m} M^T[m][j] rres_j ; M^T row m lives in rhs block 1 + m/8, row m%8
+    for (int m = wid; m < n; m += 8) {
+        const double* rowblk = rhs_base + (size_t)(1 + (m >> 3)) * NT * 64;
+        double s = 0.0;
+        for (int j = (m & ~7) + lane; j < n; j += 32) {
+            if (j >= m) s = fma(rowblk[(size_t)(j >> 3) * 64 + tile_pos(m & 7, j & 7)], out.rres[j], s);
+        }
+        s = warp_sum(s);
+        if (lane == 0) out.w[m] = s;
+    }
+    // Mop tile (Rt, K)[r][c] = M[8Rt+r][8K+c] = M^T[8K+c][8Rt+r] = rhs block (1+K), column tile Rt, (c, r)
+    const size_t ntile = (size_t)NT * (NT + 1) / 2;
+    for (size_t t = threadIdx.x; t < ntile * 64; t += blockDim.x) {
+        const size_t tl = t >> 6;
+        const int e64 = (int)(t & 63), r = e64 >> 3, c = e64 & 7;
+        // invert tl = Rt (Rt+1)/2 + K
+        int Rt = (int)((sqrt(8.0 * (double)tl + 1.0) - 1.0) * 0.5);
+        while ((size_t)Rt * (Rt + 1) / 2 > tl) --Rt;
+        while ((size_t)(Rt + 1) * (Rt + 2) / 2 <= tl) ++Rt;
+        const int K = (int)(tl - (size_t)Rt * (Rt + 1) / 2);
+        const int row = 8 * Rt + r, col = 8 * K + c;
+        double v = 0.0;
+        if (col <= row && row < n) v = rhs_base[((size_t)(1 + K) * NT + Rt) * 64 + tile_pos(c, r)];
+        out.Mop[tl * 64 + tile_pos(r, c)] = v;
+    }
+}
+
+__global__ void corr_matrix_kernel(const double* __restrict__ X, int n, int k, const double* __restrict__ theta,
+                                   const double* __restrict__ p, double* __restrict__ R) {
+    const size_t total = (size_t)n * n;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(t / n), j = (int)(t % n);
+        const int lo = min(i, j), hi = max(i, j);  // the reference fills (i <= j) and mirrors
+        double s = 0.0;
+        for (int d = 0; d < k; ++d)
+            s = __dadd_rn(s, __dmul_rn(theta[d], pow(fabs(X[(size_t)lo * k + d] - X[(size_t)hi * k + d]), p[d])));
+        R[t] = exp(-s);
+    }
+}
+
+cudaError_t launch_krig_fit(const double* X, const double* y, int n, int k, const double* theta, const double* p,
+                            FitOut out, cudaStream_t st, long long* launches) {
+    double* tiles = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&tiles, fit_tile_doubles(n) * 8, st);
+    if (e != cudaSuccess) return e;
+    krig_fit_kernel<<<1, 256, 0, st>>>(X, y, n, k, theta, p, tiles, out);
+    e = cudaGetLastError();
+    if (launches) *launches += 1;
+    if (e == cudaSuccess && out.R) {
+        int grid = (int)(((size_t)n * n + 255) / 256);
+        if (grid > 148 * 8) grid = 148 * 8;
+        corr_matrix_kernel<<<grid, 256, 0, st>>>(X, n, k, theta, p, out.R);
+        e = cudaGetLastError();
+        if (launches) *launches += 1;
+    }
+    cudaError_t e2 = cudaFreeAsync(tiles, st);
+    return e != cudaSuccess ? e : e2;
+}
+
+}  // namespace smb

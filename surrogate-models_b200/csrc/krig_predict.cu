@@ -1,0 +1,287 @@
+// Kriging prediction at many query points (replaces Kriging.predict, mylibs/kriging.py:206-220, called
+// once per query by the reference):
+//   psi_i(x) = exp(-sum_d theta_d |x_id - x_d|^p_d)           (:214-218)
+//   yhat(x)  = mu + psi . w,   w = R^-1 (y - 1 mu)             (:219, weights cached at fit time)
+// and, new functionality the north star asks for (not in the reference, SURVEY.md §8c "MSE oracle"):
+//   c = L^-1 psi = M psi ;  s^2(x) = sigma^2 [1 - c.c + (1 - b.c)^2 / (b.b)],  clamped at 0
+// The MSE path is the one real dense contraction of prediction: C[n x Q] = M[n x n] Psi[n x Q] runs on
+// DMMA with M tiles as the A operand and Psi produced *directly in B-fragment order*: lane l computes
+// psi for (sample 8K + l%4 + 4h, query l/4), which is exactly the element mma.m8n8k4 wants from it.
+// With c in hand the mean comes for free as mu + rres . c  (rres = L^-1 (y - 1 mu)).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace smb {
+
+__device__ __forceinline__ double pow_abs(double dx, double p) {
+    // abs(dx) ** p of the reference; p == 2 and p == 1 are exact in libm pow, so the shortcuts are too
+    if (p == 2.0) return dx * dx;
+    if (p == 1.0) return dx;
+    return pow(dx, p);
+}
+
+template <int KD>
+__device__ __forceinline__ double psi_one(const double* __restrict__ xs, const double* xq, const double* th,
+                                          const double* pw, int k) {
+    double s = 0.0;
+    const int kk = KD > 0 ? KD : k;
+#pragma unroll
+    for (int d = 0; d < kk; ++d) s = __dadd_rn(s, __dmul_rn(th[d], pow_abs(fabs(xs[d] - xq[d]), pw[d])));
+    return exp(-s);
+}
+
+// ------------------------------------------------------------------------------------ mean only
+template <int KD>
+__global__ void __launch_bounds__(256) krig_predict_mean_kernel(const PredictArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    double* X_s = smem;                      // [n][k]
+    double* w_s = X_s + (size_t)a.n * a.k;   // [n]
+    double* th_s = w_s + a.n;                // [KMAX]
+    double* p_s = th_s + KMAX;               // [KMAX]
+    for (int t = threadIdx.x; t < a.n * a.k; t += blockDim.x) X_s[t] = a.X[t];
+    for (int t = threadIdx.x; t < a.n; t += blockDim.x) w_s[t] = a.w[t];
+    if (threadIdx.x < a.k) {
+        th_s[threadIdx.x] = a.theta[threadIdx.x];
+        p_s[threadIdx.x] = a.p[threadIdx.x];
+    }
+    __syncthreads();
+    const int k = a.k;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < a.Nq; q += (long long)gridDim.x * blockDim.x) {
+        double xq[KD > 0 ? KD : KMAX];
+        const int kk = KD > 0 ? KD : k;
+#pragma unroll
+        for (int d = 0; d < kk; ++d) xq[d] = a.Xq[q * k + d];
+        double acc = 0.0;
+        for (int i = 0; i < a.n; ++i) acc = fma(psi_one<KD>(X_s + (size_t)i * k, xq, th_s, p_s, k), w_s[i], acc);
+        a.y_out[q] = a.mu + acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------ mean + MSE on DMMA
+// NTM >= NT = npad/8 (accumulator tiles kept in registers), QG query groups of 8 per warp pass.
+template <int NTM, int QG, int KD>
+__global__ void __launch_bounds__(256) krig_predict_mse_kernel(const PredictArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    const int NT = a.npad / 8, k = a.k;
+    const size_t ntile = (size_t)NT * (NT + 1) / 2;
+    double* M_s = smem;                              // [ntile][64]
+    double* X_s = M_s + ntile * 64;                  // [npad][k] zero padded
+    double* b_s = X_s + (size_t)a.npad * k;          // [npad]
+    double* r_s = b_s + a.npad;                      // [npad]
+    double* th_s = r_s + a.npad;                     // [KMAX]
+    double* p_s = th_s + KMAX;                       // [KMAX]
+    double* bb_s = p_s + KMAX;                       // [1]
+    for (size_t t = threadIdx.x; t < ntile * 64; t += blockDim.x) M_s[t] = a.Mop[t];
+    for (int t = threadIdx.x; t < a.npad * k; t += blockDim.x) X_s[t] = (t < a.n * k) ? a.X[t] : 0.0;
+    for (int t = threadIdx.x; t < a.npad; t += blockDim.x) {
+        b_s[t] = a.b[t];
+        r_s[t] = a.rres[t];
+    }
+    if (threadIdx.x < k) {
+        th_s[threadIdx.x] = a.theta[threadIdx.x];
+        p_s[threadIdx.x] = a.p[threadIdx.x];
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double s = 0.0;
+        for (int j = threadIdx.x; j < a.n; j += 32) s = fma(b_s[j], b_s[j], s);
+        s = warp_sum(s);
+        if (threadIdx.x == 0) bb_s[0] = s;
+    }
+    __syncthreads();
+    const double bb = bb_s[0];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int qrow = lane >> 2, kq = lane & 3;
+    const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long wglob = (long long)blockIdx.x * (blockDim.x >> 5) + wid;
+    constexpr int QW = 8 * QG;  // queries per warp pass
+    const long long npass = (a.Nq + QW - 1) / QW;
+
+    for (long long pass = wglob; pass < npass; pass += warps_total) {
+        const long long q0 = pass * QW;
+        // this lane's psi queries: q0 + 8 g + qrow
+        double xq[QG][KD > 0 ? KD : 1];
+        long long qidx[QG];
+#pragma unroll
+        for (int g = 0; g < QG; ++g) {
+            qidx[g] = q0 + 8 * g + qrow;
+            if (qidx[g] >= a.Nq) qidx[g] = a.Nq - 1;  // clamp: computed but never written
+            if (KD > 0) {
+#pragma unroll
+                for (int d = 0; d < KD; ++d) xq[g][d] = a.Xq[qidx[g] * k + d];
+            }
+        }
+        double acc[NTM][QG][2];
+#pragma unroll
+        for (int t = 0; t < NTM; ++t)
+#pragma unroll
+            for (int g = 0; g < QG; ++g) acc[t][g][0] = acc[t][g][1] = 0.0;
+
+        for (int K = 0; K < NT; ++K) {
+            double psi[QG][2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = 8 * K + kq + 4 * h;
+#pragma unroll
+                for (int g = 0; g < QG; ++g) {
+                    double v;
+                    if (KD > 0) v = psi_one<KD>(X_s + (size_t)i * k, xq[g], th_s, p_s, k);
+                    else v = psi_one<0>(X_s + (size_t)i * k, a.Xq + qidx[g] * k, th_s, p_s, k);
+                    psi[g][h] = (i < a.n) ? v : 0.0;
+                }
+            }
+#pragma unroll
+            for (int Rt = 0; Rt < NTM; ++Rt) {
+                if (Rt >= K && Rt < NT) {  // warp-uniform
+                    const double2 A = ld_frag(M_s + ((size_t)Rt * (Rt + 1) / 2 + K) * 64, lane);
+#pragma unroll
+                    for (int g = 0; g < QG; ++g) {
+                        dmma(acc[Rt][g][0], acc[Rt][g][1], A.x, psi[g][0]);
+                        dmma(acc[Rt][g][0], acc[Rt][g][1], A.y, psi[g][1]);
+                    }
+                }
+            }
+        }
+        // lane holds c[8 Rt + qrow][query 8 g + 2 kq + e]; reduce over rows
+#pragma unroll
+        for (int g = 0; g < QG; ++g) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                double cc = 0.0, bc = 0.0, rc = 0.0;
+#pragma unroll
+                for (int Rt = 0; Rt < NTM; ++Rt) {
+                    if (Rt < NT) {
+                        const double c = acc[Rt][g][e];
+                        const int row = 8 * Rt + qrow;
+                        cc = fma(c, c, cc);
+                        bc = fma(b_s[row], c, bc);
+                        rc = fma(r_s[row], c, rc);
+                    }
+                }
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    cc += __shfl_xor_sync(0xffffffffu, cc, o);
+                    bc += __shfl_xor_sync(0xffffffffu, bc, o);
+                    rc += __shfl_xor_sync(0xffffffffu, rc, o);
+                }
+                const long long q = q0 + 8 * g + 2 * kq + e;
+                if (qrow == 0 && q < a.Nq) {
+                    a.y_out[q] = a.mu + rc;
+                    const double u = 1.0 - bc;
+                    const double m = a.sigma2 * (1.0 - cc + u * u / bb);
+                    a.mse_out[q] = m > 0.0 ? m : 0.0;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ generic MSE (any n)
+// thread per query, psi staged in a global scratch [n][Q] (coalesced), M read tile-wise (L1 broadcast)
+__global__ void __launch_bounds__(256) krig_predict_mse_generic_kernel(const PredictArgs a, double* __restrict__ psi_ws) {
+    __shared__ double th_s[KMAX], p_s[KMAX], red[8];
+    const int k = a.k, n = a.n;
+    if (threadIdx.x < k) {
+        th_s[threadIdx.x] = a.theta[threadIdx.x];
+        p_s[threadIdx.x] = a.p[threadIdx.x];
+    }
+    double s = 0.0;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) s = fma(a.b[j], a.b[j], s);
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    double bb = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) bb += red[i];
+    const long long Q = (long long)gridDim.x * blockDim.x;
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    double* my = psi_ws + t;
+    for (long long q = t; q < a.Nq; q += Q) {
+        const double* xq = a.Xq + q * k;
+        for (int i = 0; i < n; ++i) my[(size_t)i * Q] = psi_one<0>(a.X + (size_t)i * k, xq, th_s, p_s, k);
+        double cc = 0.0, bc = 0.0, rc = 0.0;
+        for (int row = 0; row < n; ++row) {
+            const int Rt = row >> 3, r = row & 7;
+            const double* mrow = a.Mop + (size_t)Rt * (Rt + 1) / 2 * 64;
+            double c = 0.0;
+            for (int i = 0; i <= row; ++i) c = fma(mrow[(size_t)(i >> 3) * 64 + tile_pos(r, i & 7)], my[(size_t)i * Q], c);
+            cc = fma(c, c, cc);
+            bc = fma(a.b[row], c, bc);
+            rc = fma(a.rres[row], c, rc);
+        }
+        a.y_out[q] = a.mu + rc;
+        const double u = 1.0 - bc;
+        const double m = a.sigma2 * (1.0 - cc + u * u / bb);
+        a.mse_out[q] = m > 0.0 ? m : 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------ launchers
+template <int KD>
+static cudaError_t launch_mean(const PredictArgs& a, cudaStream_t st) {
+    const size_t smem = ((size_t)a.n * a.k + a.n + 2 * KMAX) * 8;
+    cudaError_t e = cudaFuncSetAttribute(krig_predict_mean_kernel<KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    long long grid = (a.Nq + 255) / 256;
+    const long long cap = (long long)sm_count() * 8;
+    if (grid > cap) grid = cap;
+    krig_predict_mean_kernel<KD><<<(int)grid, 256, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int NTM, int QG, int KD>
+static cudaError_t launch_mse_t(const PredictArgs& a, cudaStream_t st) {
+    const int NT = a.npad / 8;
+    const size_t smem = ((size_t)NT * (NT + 1) / 2 * 64 + (size_t)a.npad * a.k + 2 * a.npad + 2 * KMAX + 2) * 8;
+    cudaError_t e = cudaFuncSetAttribute(krig_predict_mse_kernel<NTM, QG, KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long long npass = (a.Nq + 8 * QG - 1) / (8 * QG);
+    long long grid = (npass + 7) / 8;
+    const long long cap = (long long)sm_count() * 4;
+    if (grid > cap) grid = cap;
+    krig_predict_mse_kernel<NTM, QG, KD><<<(int)grid, 256, smem, st>>>(a);
+    return cudaGetLastError();
+}
+template <int NTM, int QG>
+static cudaError_t launch_mse_k(const PredictArgs& a, cudaStream_t st) {
+    switch (a.k) {
+        case 1: return launch_mse_t<NTM, QG, 1>(a, st);
+        case 2: return launch_mse_t<NTM, QG, 2>(a, st);
+        case 3: return launch_mse_t<NTM, QG, 3>(a, st);
+        case 4: return launch_mse_t<NTM, QG, 4>(a, st);
+        default: return launch_mse_t<NTM, QG, 0>(a, st);
+    }
+}
+
+cudaError_t launch_krig_predict(const PredictArgs& a, cudaStream_t st, long long* launches) {
+    if (a.Nq <= 0) return cudaSuccess;
+    if (launches) *launches += 1;
+    if (!a.mse_out) {
+        const size_t smem = ((size_t)a.n * a.k + a.n + 2 * KMAX) * 8;
+        if (smem > smem_optin()) return cudaErrorInvalidValue;  // n*k beyond the staged-sample capacity
+        switch (a.k) {
+            case 1: return launch_mean<1>(a, st);
+            case 2: return launch_mean<2>(a, st);
+            case 3: return launch_mean<3>(a, st);
+            case 4: return launch_mean<4>(a, st);
+            case 8: return launch_mean<8>(a, st);
+            default: return launch_mean<0>(a, st);
+        }
+    }
+    const int NT = a.npad / 8;
+    if (NT <= 4) return launch_mse_k<4, 4>(a, st);
+    if (NT <= 8) return launch_mse_k<8, 2>(a, st);
+    if (NT <= 16) return launch_mse_k<16, 1>(a, st);
+    // generic path
+    long long grid = (a.Nq + 255) / 256;
+    const long long cap = (long long)sm_count() * 4;
+    if (grid > cap) grid = cap;
+    double* ws = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&ws, (size_t)grid * 256 * a.n * 8, st);
+    if (e != cudaSuccess) return e;
+    krig_predict_mse_generic_kernel<<<(int)grid, 256, 0, st>>>(a, ws);
+    e = cudaGetLastError();
+    cudaError_t e2 = cudaFreeAsync(ws, st);
+    return e != cudaSuccess ? e : e2;
+}
+
+}  // namespace smb

@@ -1,0 +1,302 @@
+// Radial-basis-function weight solve and evaluation (mylibs/rbf.py).
+//   Phi_ij = phi(a, ||x_i - x_j||_2)                      RBF._calc_coefficiants  rbf.py:67-78
+//   coeff  = Phi^-1 y                                      np.linalg.solve          rbf.py:79
+//   f(x)   = sum_i coeff_i phi(a, ||x - x_i||_2)           RBF.predict              rbf.py:85-103
+// kernels (rbf.py:105-118): 0 lin r | 1 cubic r^3 | 2 gaus e^-(a r)^2 | 3 mq sqrt(1+(a r)^2)
+//                           4 imq (1 + r^2)^(a/2)   (the reference's own formula, kept as is)
+// The gaussian kernel matrix is SPD: it goes through the same DMMA tile Cholesky as the Kriging
+// likelihood, followed by a tile back-substitution.  The other kernels are not definite and use LU with
+// partial pivoting (what np.linalg.solve does), as does a gaussian matrix that is not numerically SPD.
+#include "tile_chol.cuh"
+#include "kernels.h"
+
+namespace smb {
+
+__device__ __forceinline__ double rbf_phi(int kind, double a, double r) {
+    switch (kind) {
+        case 0: return r;
+        case 1: return r * r * r;
+        case 2: { const double t = a * r; return exp(-(t * t)); }
+        case 3: { const double t = a * r; return sqrt(1.0 + t * t); }
+        default: return pow(1.0 + r * r, 0.5 * a);
+    }
+}
+
+__device__ __forceinline__ double rbf_dist(const double* __restrict__ xi, const double* __restrict__ xj, int k) {
+    double s = 0.0;
+    for (int d = 0; d < k; ++d) {
+        const double dx = xi[d] - xj[d];
+        s = __dadd_rn(s, __dmul_rn(dx, dx));  // radSum += (dx) ** 2.
+    }
+    return sqrt(s);
+}
+
+struct RbfEntry {
+    const double* X;
+    int k, n, kind;
+    double a;
+    __device__ __forceinline__ double one(int i, int j) const {
+        if (i >= n || j >= n) return (i == j) ? 1.0 : 0.0;
+        return rbf_phi(kind, a, rbf_dist(X + (size_t)min(i, j) * k, X + (size_t)max(i, j) * k, k));
+    }
+    __device__ __forceinline__ void operator()(int i, int j, double& v0, double& v1) const {
+        v0 = one(i, j);
+        v1 = one(i, j + 1);
+    }
+};
+struct RbfRhs {  // row 0 = y^T
+    const double* y;
+    int n;
+    __device__ __forceinline__ void operator()(int rr, int j, double& v0, double& v1) const {
+        v0 = (rr == 0 && j < n) ? y[j] : 0.0;
+        v1 = (rr == 0 && j + 1 < n) ? y[j + 1] : 0.0;
+    }
+};
+
+// SPD solve: Phi = L L^T (tile engine), a = L^-1 y, then L^T c = a by tile back-substitution.
+__global__ void __launch_bounds__(256) rbf_fit_chol_kernel(const double* __restrict__ X, const double* __restrict__ y,
+                                                           int n, int k, int kind, double a,
+                                                           double* __restrict__ tiles, double* __restrict__ coeff,
+                                                           double* __restrict__ xwork, int* __restrict__ info) {
+    __shared__ double wscr[8 * 64];
+    __shared__ double cj[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int NT = (n + 7) / 8, npad = NT * 8;
+    const RbfEntry e{X, k, n, kind, a};
+    const RbfRhs rhs{y, n};
+    const CholResult res = tile_cholesky<8, 4, false>(tiles, NT, 1, e, rhs, wscr + wid * 64, wid, lane);
+    if (!res.ok) {
+        if (threadIdx.x == 0) *info = -1;  // not numerically SPD: caller falls back to LU
+        return;
+    }
+    const double* rhs_row = tiles + (size_t)NT * (NT + 1) / 2 * 64;
+    for (int j = threadIdx.x; j < npad; j += blockDim.x)
+        xwork[j] = (j < n) ? rhs_row[(size_t)(j >> 3) * 64 + tile_pos(0, j & 7)] : 0.0;
+    __syncthreads();
+    for (int J = NT - 1; J >= 0; --J) {
+        const double* rowJ = tiles + (size_t)J * (J + 1) / 2 * 64;
+        if (threadIdx.x < 8) {  // c_J = W_J^T s_J
+            const double* W = rowJ + (size_t)J * 64;
+            double s = 0.0;
+            for (int r = 0; r < 8; ++r) s = fma(W[tile_pos(r, threadIdx.x)], xwork[8 * J + r], s);
+            cj[threadIdx.x] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x < 8) xwork[8 * J + threadIdx.x] = cj[threadIdx.x];
+        // s_{I'} -= L_{J,I'}^T c_J for every I' < J
+        for (int t = threadIdx.x; t < 8 * J; t += blockDim.x) {
+            const double* T = rowJ + (size_t)(t >> 3) * 64;
+            const int c = t & 7;
+            double s = xwork[t];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) s = fma(-T[tile_pos(r, c)], cj[r], s);
+            xwork[t] = s;
+        }
+        __syncthreads();
+    }
+    for (int j = threadIdx.x; j < n; j += blockDim.x) coeff[j] = xwork[j];
+    if (threadIdx.x == 0) *info = 0;
+}
+
+// ------------------------------------------------------------------------------------ LU with partial pivoting
+__global__ void rbf_matrix_kernel(const double* __restrict__ X, int n, int k, int kind, double a, double* __restrict__ A) {
+    const size_t total = (size_t)n * n;  // column-major A[i + j n]; symmetric, so the order is immaterial
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(t % n), j = (int)(t / n);
+        A[t] = rbf_phi(kind, a, rbf_dist(X + (size_t)min(i, j) * k, X + (size_t)max(i, j) * k, k));
+    }
+}
+
+// one CTA: pivot search in column c, row swap (whole rows, and the rhs), scale the sub-column
+__global__ void __launch_bounds__(1024) lu_pivot_kernel(double* __restrict__ A, double* __restrict__ rhs, int n, int c,
+                                                        int* __restrict__ info) {
+    __shared__ double bv[32];
+    __shared__ int bi[32];
+    __shared__ int piv_s;
+    double* col = A + (size_t)c * n;
+    double best = -1.0;
+    int besti = c;
+    for (int i = c + threadIdx.x; i < n; i += blockDim.x) {
+        const double v = fabs(col[i]);
+        if (v > best) { best = v; besti = i; }  // first maximum per thread (increasing i)
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { bv[threadIdx.x >> 5] = best; bi[threadIdx.x >> 5] = besti; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        best = (threadIdx.x < (blockDim.x >> 5)) ? bv[threadIdx.x] : -1.0;
+        besti = (threadIdx.x < (blockDim.x >> 5)) ? bi[threadIdx.x] : n;
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+            if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+        }
+        if (threadIdx.x == 0) {
+            piv_s = besti;
+            if (!(best > 0.0) && *info == 0) *info = c + 1;  // exactly singular (LAPACK info > 0)
+        }
+    }
+    __syncthreads();
+    const int piv = piv_s;
+    if (piv != c) {
+        for (int j = threadIdx.x; j < n; j += blockDim.x) {
+            const double t = A[(size_t)j * n + c];
+            A[(size_t)j * n + c] = A[(size_t)j * n + piv];
+            A[(size_t)j * n + piv] = t;
+        }
+        if (threadIdx.x == 0) { const double t = rhs[c]; rhs[c] = rhs[piv]; rhs[piv] = t; }
+    }
+    __syncthreads();
+    const double d = 1.0 / col[c];
+    for (int i = c + 1 + threadIdx.x; i < n; i += blockDim.x) col[i] *= d;
+}
+
+// trailing update A[i][j] -= l_i u_j and the forward-substituted rhs
+__global__ void __launch_bounds__(256) lu_update_kernel(double* __restrict__ A, double* __restrict__ rhs, int n, int c) {
+    const int m = n - c - 1;
+    const double* l = A + (size_t)c * n + c + 1;
+    const size_t total = (size_t)m * m;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(t % m), j = (int)(t / m);
+        double* colj = A + (size_t)(c + 1 + j) * n;
+        colj[c + 1 + i] = fma(-l[i], colj[c], colj[c + 1 + i]);
+    }
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i < m; i += blockDim.x) rhs[c + 1 + i] = fma(-l[i], rhs[c], rhs[c + 1 + i]);
+}
+
+// U x = z, single CTA, column oriented
+__global__ void __launch_bounds__(1024) lu_backsolve_kernel(const double* __restrict__ A, double* __restrict__ rhs, int n) {
+    __shared__ double xj;
+    for (int j = n - 1; j >= 0; --j) {
+        if (threadIdx.x == 0) {
+            xj = rhs[j] / A[(size_t)j * n + j];
+            rhs[j] = xj;
+        }
+        __syncthreads();
+        const double* col = A + (size_t)j * n;
+        for (int i = threadIdx.x; i < j; i += blockDim.x) rhs[i] = fma(-col[i], xj, rhs[i]);
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_rbf_fit(const double* X, const double* y, int n, int k, int kind, double a, double* coeff,
+                           int* info, cudaStream_t st, long long* launches) {
+    cudaError_t e;
+    const int NT = (n + 7) / 8;
+    int h_info = -1;
+    if (kind == 2) {
+        double *tiles = nullptr, *xwork = nullptr;
+        e = cudaMallocAsync((void**)&tiles, chol_tiles(NT, 1) * 512, st);
+        if (e != cudaSuccess) return e;
+        e = cudaMallocAsync((void**)&xwork, (size_t)NT * 8 * 8, st);
+        if (e != cudaSuccess) return e;
+        rbf_fit_chol_kernel<<<1, 256, 0, st>>>(X, y, n, k, kind, a, tiles, coeff, xwork, info);
+        if (launches) *launches += 1;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpyAsync(&h_info, info, sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return e;
+        e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return e;
+        cudaFreeAsync(tiles, st);
+        cudaFreeAsync(xwork, st);
+        if (h_info == 0) return cudaSuccess;
+    }
+    // LU with partial pivoting on the dense column-major matrix
+    double* A = nullptr;
+    e = cudaMallocAsync((void**)&A, (size_t)n * n * 8, st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(info, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    int grid = (int)(((size_t)n * n + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    rbf_matrix_kernel<<<grid, 256, 0, st>>>(X, n, k, kind, a, A);
+    e = cudaMemcpyAsync(coeff, y, (size_t)n * 8, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return e;
+    for (int c = 0; c < n; ++c) {
+        lu_pivot_kernel<<<1, n - c > 2048 ? 1024 : 256, 0, st>>>(A, coeff, n, c, info);
+        const int m = n - c - 1;
+        if (m > 0) {
+            int g = (int)(((size_t)m * m + 255) / 256);
+            if (g > 148 * 8) g = 148 * 8;
+            lu_update_kernel<<<g, 256, 0, st>>>(A, coeff, n, c);
+        }
+    }
+    lu_backsolve_kernel<<<1, n > 2048 ? 1024 : 256, 0, st>>>(A, coeff, n);
+    if (launches) *launches += 2 * (long long)n + 2;
+    e = cudaGetLastError();
+    cudaError_t e2 = cudaFreeAsync(A, st);
+    return e != cudaSuccess ? e : e2;
+}
+
+// ------------------------------------------------------------------------------------ evaluation
+// Samples + coefficients are staged through shared memory in chunks; each thread owns one query.
+constexpr int RBF_CHUNK = 2048;
+template <int KD>
+__global__ void __launch_bounds__(256) rbf_predict_kernel(const double* __restrict__ X, int n, int k, int kind, double a,
+                                                          const double* __restrict__ coeff,
+                                                          const double* __restrict__ Xq, long long Nq,
+                                                          double* __restrict__ y_out) {
+    extern __shared__ __align__(16) double smem[];
+    double* X_s = smem;                          // [chunk][k]
+    double* c_s = X_s + (size_t)RBF_CHUNK * k;   // [chunk]
+    const int kk = KD > 0 ? KD : k;
+    const long long Q = (long long)gridDim.x * blockDim.x;
+    const long long nrounds = (Nq + Q - 1) / Q;
+    for (long long rd = 0; rd < nrounds; ++rd) {
+        const long long q = rd * Q + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+        const bool live = q < Nq;
+        double xq[KD > 0 ? KD : KMAX];
+#pragma unroll
+        for (int d = 0; d < kk; ++d) xq[d] = live ? Xq[q * k + d] : 0.0;
+        double res = 0.0;
+        for (int i0 = 0; i0 < n; i0 += RBF_CHUNK) {
+            const int m = min(RBF_CHUNK, n - i0);
+            __syncthreads();
+            for (int t = threadIdx.x; t < m * k; t += blockDim.x) X_s[t] = X[(size_t)i0 * k + t];
+            for (int t = threadIdx.x; t < m; t += blockDim.x) c_s[t] = coeff[i0 + t];
+            __syncthreads();
+            for (int i = 0; i < m; ++i) {
+                double s = 0.0;
+#pragma unroll
+                for (int d = 0; d < kk; ++d) {
+                    const double dx = xq[d] - X_s[(size_t)i * k + d];
+                    s = __dadd_rn(s, __dmul_rn(dx, dx));
+                }
+                res = fma(c_s[i], rbf_phi(kind, a, sqrt(s)), res);  // res += coeff_i * phi
+            }
+        }
+        if (live) y_out[q] = res;
+    }
+}
+
+cudaError_t launch_rbf_predict(const double* X, int n, int k, int kind, double a, const double* coeff,
+                               const double* Xq, long long Nq, double* y_out, cudaStream_t st, long long* launches) {
+    if (Nq <= 0) return cudaSuccess;
+    const size_t smem = (size_t)RBF_CHUNK * (k + 1) * 8;
+    long long grid = (Nq + 255) / 256;
+    const long long cap = (long long)sm_count() * 4;
+    if (grid > cap) grid = cap;
+    cudaError_t e;
+#define SMB_RBF_LAUNCH(KD)                                                                                          \
+    e = cudaFuncSetAttribute(rbf_predict_kernel<KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+    if (e != cudaSuccess) return e;                                                                                 \
+    rbf_predict_kernel<KD><<<(int)grid, 256, smem, st>>>(X, n, k, kind, a, coeff, Xq, Nq, y_out);
+    switch (k) {
+        case 1: SMB_RBF_LAUNCH(1) break;
+        case 2: SMB_RBF_LAUNCH(2) break;
+        case 3: SMB_RBF_LAUNCH(3) break;
+        case 4: SMB_RBF_LAUNCH(4) break;
+        default: SMB_RBF_LAUNCH(0) break;
+    }
+#undef SMB_RBF_LAUNCH
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
+}  // namespace smb
