@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""Headline benchmark: batched concentrated-log-likelihood evaluations per second (BASELINE.json
+configs[1]: 2-D Kriging, n = 64 Halton samples, 10^6 (theta, p) candidates = generate_grid(func, 2, 40, 25))
+plus, as a secondary figure, Kriging predictions (value + MSE) per second on the kriging_r3 model.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one pass of the hot path over one batch: 10^6 candidates per GPU.  N > 1 (torchrun): weak
+scaling -- rank r evaluates candidates [r 10^6, (r+1) 10^6) of a finer p-grid and the only collective is
+the (nll, index) all_gather of the first-minimum reduction.  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, 'surrogate-models_b200')):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+N_SAMPLES, K_DIM, T_SEC, CAND_PER_GPU = 64, 2, 40, 1000000
+METRIC = 'kriging likelihood evaluations/s (n=64, k=2)'
+
+
+def p_sections_for(world):
+    """smallest P with 40^2 P^2 >= world * 10^6 (P = 25 at world 1: exactly the BASELINE grid)"""
+    P = 25
+    while (T_SEC ** K_DIM) * (P ** K_DIM) < world * CAND_PER_GPU:
+        P += 1
+    return P
+
+
+def flops_like(n, k):
+    """algorithmic flops of one likelihood evaluation, Cholesky form: n^3/3 + (k+2) n^2"""
+    return n ** 3 / 3.0 + (k + 2) * n ** 2
+
+
+def fp64_peaks():
+    """measured fp64 peaks of this pool's B200 (tools/fp64_peaks.cu -> profiles/r01_fp64_peaks.json);
+    MEASURED_PEAKS.json carries HBM and bf16 only"""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r01_fp64_peaks.json')) as f:
+            d = json.load(f)
+        return d['dmma_m8n8k4_acc8_tflops'], d['exp_gops'], 'measured (profiles/r01_fp64_peaks.json)'
+    except Exception:
+        return 37.0, 818.0, 'fallback (148 SM x 64 FMA/clk x 1.965 GHz)'
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def _cpu_chunk(args):
+    """reference algorithm on `count` candidates starting at flat index lo (statement-by-statement port:
+    interpreted correlation loop + np.linalg.inv + slogdet, mylibs/kriging.py:66-116)"""
+    lo, count, P, mode = args
+    os.environ['OPENBLAS_NUM_THREADS'] = '1'
+    from oracle import numpy_oracle as orc
+    from sm_b200 import workloads
+    X, y = workloads.c2_halton64()
+    e, q = orc.grid_candidates(K_DIM, T_SEC, P, lo, lo + count)
+    f = orc.nll_lu_loops if mode == 'loops' else orc.nll_lu
+    t0 = time.perf_counter()
+    out = 0.0
+    for c in range(count):
+        try:
+            v = f(X, y, [10. ** t for t in e[c]], q[c])
+        except np.linalg.LinAlgError:
+            v = float('inf')
+        out += 0.0 if not np.isfinite(v) else v
+    return time.perf_counter() - t0, out
+
+
+def cpu_rate(per_proc, mode, procs, P=25, offset=250000):
+    """aggregate evaluations/s of the CPU port on `procs` processes, `per_proc` candidates each, taken from
+    the middle of the grid (well-conditioned and ill-conditioned candidates cost the same)"""
+    import multiprocessing as mp
+    jobs = [(offset + i * per_proc, per_proc, P, mode) for i in range(procs)]
+    t0 = time.perf_counter()
+    with mp.get_context('spawn').Pool(procs) as pool:
+        pool.map(_cpu_chunk, [(offset, 2, P, mode)] * procs)  # warm the workers (imports, BLAS init)
+        t0 = time.perf_counter()
+        pool.map(_cpu_chunk, jobs)
+        dt = time.perf_counter() - t0
+    return procs * per_proc / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count()
+    per_proc = 120  # ~0.6 s per process per step at ~5 ms / evaluation
+    for _ in range(args.warmup):
+        cpu_rate(8, 'loops', cores)
+    rates, t_all = [], 0.0
+    for _ in range(args.steps):
+        r, dt = cpu_rate(per_proc, 'loops', cores)
+        rates.append(r)
+        t_all += dt
+    value = float(np.mean(rates))
+    vec, _ = cpu_rate(600, 'vectorised', cores)
+    sample = (f'{per_proc} candidates x {cores} processes per step from the middle of the 40x40x25x25 grid; '
+              'statement-by-statement port of mylibs/kriging.py:66-116 (interpreted R loop + inv + slogdet)')
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'evals/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * t_all / max(1, args.steps),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'C2: n=64 Halton samples, k=2, generate_grid(40,25) candidates (bounded sample)'},
+        'cpu_baseline': {'value': value, 'unit': 'evals/s', 'cores': cores, 'kind': 'port', 'sample': sample,
+                         'vectorised_numpy_port_value': vec},
+        'e2e': {'value': value, 'unit': 'evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+class ClockSampler:
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+             'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+        self.path = tempfile.mktemp(prefix='clocks_', suffix='.csv')
+
+    def start(self):
+        try:
+            self.fh = open(self.path, 'w')
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.index)], stdout=self.fh,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in open(self.path):
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm), sm_mhz_min=float(min(sm)))
+        return out
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as td
+    from sm_b200 import _cabi, device, dist, workloads
+    from mylibs.kriging import Kriging, grid_axes
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local)
+    if world > 1:
+        td.init_process_group('nccl', device_id=torch.device('cuda', local))
+    L = _cabi.lib()
+
+    X, y = workloads.c2_halton64()
+    P = p_sections_for(world)
+    lo = rank * CAND_PER_GPU
+    krig = Kriging(X, y)
+    d = krig._dev()
+    th_axis, p_axis = grid_axes(T_SEC, P)
+    th_lin_h = np.array([10. ** e for e in th_axis])
+    th_lin, pa = device.to_dev(th_lin_h), device.to_dev(p_axis)
+    nll = device.empty(CAND_PER_GPU)
+    bv, bi = device.empty(1), device.empty(1, dtype=torch.int64)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device='cuda')  # 256 MiB > 126 MB L2
+    stream = device.stream()
+
+    def step():
+        _cabi.check(L.sm_krig_nll_grid(device.ptr(d['X']), device.ptr(d['y']), N_SAMPLES, K_DIM, device.ptr(th_lin),
+                                       T_SEC, device.ptr(pa), P, lo, CAND_PER_GPU, device.ptr(nll), device.ptr(bv),
+                                       device.ptr(bi), stream))
+        if world > 1:
+            return dist.global_first_min(bv.item(), bi.item())
+        return None
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    n0 = _cabi.launch_count()
+    barrier()
+    for e0, e1 in ev:
+        flush.zero_()  # evict L2 between timed iterations (untimed)
+        e0.record()
+        step()
+        e1.record()
+    barrier()
+    launches = _cabi.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = float(np.sum([a.elapsed_time(b) for a, b in ev]))
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * CAND_PER_GPU / (ms_per_step * 1e-3)
+
+    # ---- kernel-only timing of the dominant kernel for the roofline (same stream, CUDA events)
+    best_val, best_idx = float(bv.item()), int(bi.item())
+    kms = []
+    for _ in range(max(3, min(args.steps, 10))):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _cabi.check(L.sm_krig_nll_grid(device.ptr(d['X']), device.ptr(d['y']), N_SAMPLES, K_DIM, device.ptr(th_lin),
+                                       T_SEC, device.ptr(pa), P, lo, CAND_PER_GPU, device.ptr(nll), None, None, stream))
+        b.record()
+        torch.cuda.synchronize()
+        kms.append(a.elapsed_time(b))
+    kernel_ms = float(np.mean(kms))  # table build (~20 us) + likelihood kernel
+    peak_tf, exp_gops, peak_src = fp64_peaks()
+    fl = flops_like(N_SAMPLES, K_DIM) * CAND_PER_GPU
+    n_exp = N_SAMPLES * (N_SAMPLES - 1) / 2 * CAND_PER_GPU
+    achieved = fl / (kernel_ms * 1e-3) / 1e12
+    t_bound = fl / (peak_tf * 1e12) + n_exp / (exp_gops * 1e9)
+    roofline = {
+        'bound': 'tensor', 'bound_detail': 'fp64 pipe (DMMA / DFMA share one 37 TFLOP/s peak); not HBM',
+        'kernel': 'krig_nll_kernel<1,false,0>', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
+        'frac': achieved / peak_tf, 'peak_source': peak_src, 'traffic': None,
+        'flops_per_eval': flops_like(N_SAMPLES, K_DIM), 'exp_per_eval': N_SAMPLES * (N_SAMPLES - 1) / 2,
+        'kernel_ms': kernel_ms, 'frac_two_resource': t_bound / (kernel_ms * 1e-3),
+        'hbm_gbs_achieved': (8.0 * CAND_PER_GPU) / (kernel_ms * 1e-3) / 1e9,
+    }
+
+    # ---- end to end through the host-buffer C-ABI (pinned host memory, copies inside the timed region)
+    Xh = torch.from_numpy(np.ascontiguousarray(X)).pin_memory()
+    yh = torch.from_numpy(np.ascontiguousarray(y)).pin_memory()
+    thh = torch.from_numpy(th_lin_h).pin_memory()
+    pah = torch.from_numpy(np.ascontiguousarray(p_axis)).pin_memory()
+    nllh = torch.empty(CAND_PER_GPU, dtype=torch.float64).pin_memory()
+    bvh = torch.empty(1, dtype=torch.float64).pin_memory()
+    bih = torch.empty(1, dtype=torch.int64).pin_memory()
+
+    def e2e_step():
+        _cabi.check(L.sm_krig_nll_grid_host(Xh.data_ptr(), yh.data_ptr(), N_SAMPLES, K_DIM, thh.data_ptr(), T_SEC,
+                                            pah.data_ptr(), P, lo, CAND_PER_GPU, nllh.data_ptr(), bvh.data_ptr(),
+                                            bih.data_ptr()))
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {'value': world * CAND_PER_GPU * args.steps / e2e_s, 'unit': 'evals/s',
+           'h2d_bytes_per_step': int(8 * (X.size + y.size + T_SEC + P)), 'd2h_bytes_per_step': int(8 * CAND_PER_GPU + 16),
+           'api': 'sm_krig_nll_grid_host (pinned host buffers)'}
+    assert int(bih.item()) == best_idx
+
+    # ---- secondary: predictions/s (value + MSE) on the kriging_r3 model, queries resident in HBM
+    X5, y5 = workloads.c5_kriging_r3()
+    k5 = Kriging(X5, y5)
+    k5.update_param([0.05, 0.05], [1.9, 1.9])
+    m = 3162  # 3162^2 ~ 1e7 mesh points per GPU over [-2, 12]^2
+    xq = device.to_dev(workloads.c5_query_mesh(m))
+    for _ in range(2):
+        k5.predict_device(xq, True)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    k5.predict_device(xq, True)
+    b.record()
+    torch.cuda.synchronize()
+    pred_ms = a.elapsed_time(b)
+    secondary = {'metric': 'kriging predictions/s (value+MSE, n=36, k=2, p=1.9)', 'value': world * m * m / (pred_ms * 1e-3),
+                 'unit': 'predictions/s', 'queries_per_gpu': m * m, 'ms': pred_ms,
+                 'hbm_gbs_achieved': m * m * 32 / (pred_ms * 1e-3) / 1e9}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count()
+            per_proc = 150
+            v_loops, dt1 = cpu_rate(per_proc, 'loops', cores)
+            v_vec, dt2 = cpu_rate(1500, 'vectorised', cores)
+            cpu = {'value': v_loops, 'unit': 'evals/s', 'cores': cores, 'kind': 'port',
+                   'sample': f'{per_proc} candidates x {cores} processes from the middle of the grid ({dt1:.1f} s); '
+                             'statement-by-statement port of mylibs/kriging.py:66-116 (interpreted R loop, inv, slogdet)',
+                   'vectorised_numpy_port_value': v_vec,
+                   'vectorised_sample': f'1500 candidates x {cores} processes ({dt2:.1f} s); numpy-vectorised R build + inv + slogdet'}
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'evals/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': f'C2: n=64 Halton samples on [0,10]^2 (y=f_3d), k=2, 1e6 (theta,p) candidates per GPU '
+                                   f'= generate_grid(func,2,{T_SEC},{P}) flat range [r*1e6,(r+1)*1e6)',
+                       'candidates_per_gpu': CAND_PER_GPU, 'l2': 'flushed (256 MiB write) between timed steps',
+                       'parallelism': f'candidate-sharded x{world}; all_gather of (nll_min, index) only'},
+            'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline,
+            'cpu_baseline': cpu, 'secondary': secondary,
+            'result': {'best_idx': best_idx, 'best_nll': best_val},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        td.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

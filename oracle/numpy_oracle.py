@@ -132,7 +132,13 @@ def nll_opti_exp(X, y, params, form='lu'):
     k = params.shape[0] // 2
     theta = [10. ** e for e in params[:k]]  # scalar pow like the reference (:133-136)
     f = nll_lu if form == 'lu' else nll_chol
-    return f(X, y, theta, params[k:])
+    try:
+        return f(X, y, theta, params[k:])
+    except np.linalg.LinAlgError:
+        # exactly singular LU: the reference swallows the exception and reports the likelihood of the
+        # PREVIOUS candidate (stale _cor_mat/_core_mat_inv, kriging.py:78-83).  The oracle -- like the
+        # GPU path -- reports +inf instead (DESIGN.md "Numerical contract").
+        return float('inf')
 
 
 def nll_batch(X, y, log10_theta, p, form='lu'):
@@ -141,10 +147,7 @@ def nll_batch(X, y, log10_theta, p, form='lu'):
     p = np.atleast_2d(np.asarray(p, dtype=np.float64))
     out = np.empty(log10_theta.shape[0])
     for c in range(out.shape[0]):
-        try:
-            out[c] = nll_opti_exp(X, y, np.concatenate([log10_theta[c], p[c]]), form)
-        except np.linalg.LinAlgError:
-            out[c] = float('inf')
+        out[c] = nll_opti_exp(X, y, np.concatenate([log10_theta[c], p[c]]), form)
     return out
 
 

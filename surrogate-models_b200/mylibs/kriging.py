@@ -1,0 +1,464 @@
+"""n-dimensional ordinary Kriging on one B200 -- drop-in for the reference's ``mylibs/kriging.py``.
+
+Same class, methods, attributes and error behaviour as the reference (file:line cited per method); the
+arithmetic runs in hand-written sm_100a kernels behind the C-ABI of ``include/surrogate_b200.h``.  There
+is no CPU path: without a CUDA device every compute call raises ``SurrogateB200Error``.
+
+Differences that are deliberate (DESIGN.md "Numerical contract"):
+  * the likelihood is evaluated in Cholesky form; a correlation matrix that is not numerically SPD gives
+    ``+inf`` where the reference (LU inverse + log|det|, kriging.py:79,100) returns rounding noise;
+  * ``predict`` uses weights cached at ``update_param`` time instead of recomputing ``psi^T R^-1`` per call;
+  * additive batched entry points: ``likelihood_batch``, ``likelihood_grid``, ``grid_search``,
+    ``predict_batch`` (value and MSE).
+"""
+import numpy as np
+from scipy.optimize import basinhopping, minimize
+
+from mylibs.likeli_optimizer import LikeliOptimizer
+from myutils.time_track import TimeTrack
+from sm_b200 import _cabi, device, dist
+
+VERBOSE = False
+
+
+class Kriging:
+
+    def __init__(self, known_in, known_val):
+        """
+        :param known_in: list of lists with input sample points
+        :param known_val: list of results for the known_in
+        (reference: mylibs/kriging.py:28-44)
+        """
+        self._known_in = np.array(known_in, dtype=np.float64)
+        self._known_val = np.array(known_val, dtype=np.float64)
+        if len(self._known_in.shape) == 1:
+            self._known_in = self._known_in.reshape((self._known_in.shape[0], 1))
+        self._k = self._known_in.shape[1]
+        self._n = self._known_in.shape[0]
+        self._theta = 1. * np.ones((self._k, 1)).flatten()
+        self._p = 2. * np.ones((self._k, 1)).flatten()
+        self._mu = None
+        self._mat_u = None
+        # device state (created on first use)
+        self._d = None
+        self._fit = None
+        self._cor_mat_cache = None
+        self._cor_mat_inv_cache = None
+
+    # ------------------------------------------------------------------ device plumbing
+    def _dev(self):
+        if self._d is None:
+            device.require_cuda()
+            self._d = dict(X=device.to_dev(self._known_in), y=device.to_dev(self._known_val))
+        return self._d
+
+    def _run_fit(self, want_R=False):
+        """sm_krig_fit at the current (theta, p): the state update_param leaves behind."""
+        L = _cabi.lib()
+        d = self._dev()
+        n, k = self._n, self._k
+        npad = L.sm_krig_npad(n)
+        th, pw = device.to_dev(self._theta), device.to_dev(self._p)
+        if th.numel() != k or pw.numel() != k:
+            raise ValueError('theta and p need one entry per input dimension')
+        f = dict(theta=th, p=pw, scalars=device.empty(4), w=device.empty(n), b=device.empty(npad),
+                 rres=device.empty(npad), Mop=device.empty(L.sm_krig_mop_doubles(n)),
+                 R=device.empty((n, n)) if want_R else None)
+        _cabi.check(L.sm_krig_fit(device.ptr(d['X']), device.ptr(d['y']), n, k, device.ptr(th), device.ptr(pw),
+                                  device.ptr(f['scalars']), device.ptr(f['w']), device.ptr(f['b']),
+                                  device.ptr(f['rres']), device.ptr(f['Mop']), device.ptr(f['R']),
+                                  device.stream()))
+        sc = f['scalars'].cpu().numpy()  # synchronises
+        f['nll'], f['mu'], f['sigma2'], f['ok'] = float(sc[0]), float(sc[1]), float(sc[2]), sc[3] == 0.0
+        return f
+
+    # ------------------------------------------------------------------ reference API
+    def train(self):
+        """trains the surrogate (reference: kriging.py:46-51)"""
+        self.optimize()
+
+    def update_param(self, theta, p):
+        """
+        updates the parameters of the surrogate model (reference: kriging.py:53-63)
+        :param theta: vector of theta parameters for each entry one (from range [1e-5 .. 1e+5])
+        :param p: vector of p parameters for each entry one (from range[1 ..2])
+        """
+        self._theta = np.array(theta, dtype=np.float64)
+        self._p = np.array(p, dtype=np.float64)
+        self._calc_cormat()
+        self._calc_mu()
+
+    def _calc_cormat(self):
+        """Builds R on the device, factorises it and caches the fitted state (reference: kriging.py:66-84).
+        Returns nothing heavy: the dense matrix is materialised lazily through ``_cor_mat``."""
+        self._cor_mat_cache = None
+        self._cor_mat_inv_cache = None
+        self._fit = self._run_fit()
+        if not self._fit['ok'] and VERBOSE:
+            print('ERROR: correlation matrix is not numerically positive definite')
+
+    def _calc_mu(self):
+        """mu = 1^T R^-1 y / 1^T R^-1 1 (reference: kriging.py:86-93); computed by the fit kernel."""
+        if self._fit is None:
+            self._calc_cormat()
+        self._mu = np.float64(self._fit['mu'])
+        return self._mu
+
+    @property
+    def _cor_mat(self):
+        """Dense correlation matrix (reference attribute, kriging.py:80); None before update_param."""
+        if self._fit is None:
+            return None
+        if self._cor_mat_cache is None:
+            self._cor_mat_cache = self._run_fit(want_R=True)['R'].cpu().numpy()
+        return self._cor_mat_cache
+
+    @property
+    def _core_mat_inv(self):
+        """R^-1 = L^-T L^-1 assembled on the device from the cached factor (reference attribute,
+        kriging.py:79).  Compatibility accessor, not on the hot path."""
+        if self._fit is None:
+            return None
+        if self._cor_mat_inv_cache is None:
+            import torch
+            n = self._n
+            nt = (n + 7) // 8
+            mop = self._fit['Mop'].view(-1, 8, 8)  # operand order: [r][2 (c & 3) + (c >> 2)]
+            perm = torch.tensor([0, 4, 1, 5, 2, 6, 3, 7], device=mop.device)  # position -> column
+            tiles = torch.empty_like(mop)
+            tiles[:, :, perm] = mop
+            M = torch.zeros((nt * 8, nt * 8), dtype=torch.float64, device=mop.device)
+            t = 0
+            for i in range(nt):
+                for j in range(i + 1):
+                    M[8 * i:8 * i + 8, 8 * j:8 * j + 8] = tiles[t]
+                    t += 1
+            M = M[:n, :n]
+            self._cor_mat_inv_cache = (M.T @ M).cpu().numpy()
+        return self._cor_mat_inv_cache
+
+    def calc_likelihood(self):
+        """
+        negative concentrated log-likelihood at the current parameters (reference: kriging.py:95-116)
+        :return: neg. log. likelihood, or inf when R is not numerically SPD / sigma^2 is invalid
+        """
+        if self._fit is None:
+            self._calc_cormat()
+        nll = self._fit['nll']
+        if np.isnan(nll):
+            return float('inf')
+        return np.float64(nll)
+
+    def _calc_likelihood_opti_theta_only(self, params, *args):
+        """(reference: kriging.py:118-121)"""
+        self.update_param(params, args[0])
+        return self.calc_likelihood()
+
+    def _calc_likelihood_opti(self, params, *args):
+        """(reference: kriging.py:123-128)"""
+        self.update_param(params[0:self._k], params[self._k:])
+        neg_ln_like = self.calc_likelihood()
+        if getattr(self, 'records', None) is not None:
+            self.records.append(params)
+        return neg_ln_like
+
+    def _calc_likelihood_opti_exp(self, params, *args):
+        """objective of the optimisers: params = [log10 theta_1..k, p_1..k] (reference: kriging.py:130-141)"""
+        if np.isnan(params).any():
+            return float('nan')
+        exps = params[0:self._k]
+        thetas = []
+        for e in exps:
+            thetas.append(10.**e)
+        self.update_param(thetas, params[self._k:])
+        neg_ln_like = self.calc_likelihood()
+        if getattr(self, 'records', None) is not None:
+            self.records.append(params)
+        return neg_ln_like
+
+    def optimize_theta_only(self):
+        """(reference: kriging.py:143-152)"""
+        x0 = np.ones((self._k, 1)).flatten()
+        bnds = [(0.0001, 1000.) for _ in range(self._k)]
+        opt = {'disp': True, 'maxiter': 99999}
+        res = minimize(self._calc_likelihood_opti_theta_only, x0, args=self._p, method='SLSQP', tol=1e-6,
+                       options=opt, bounds=bnds)
+        self._theta = res.x
+
+    def optimize(self, init_guess=None, opti_algo='grid', record_data=False):
+        """
+        runs automatic optimization of thetas and ps (reference: kriging.py:154-204)
+        :param init_guess: list of input values for an initial guess
+        :param opti_algo: 'grid' (LikeliOptimizer: batched GPU grid + SLSQP) or 'basin' (scipy basin-hopping)
+        :param record_data: record every evaluated parameter vector in self.records
+        """
+        timer = TimeTrack('optiTimer')
+        self.records = None
+        if record_data:
+            self.records = []
+        if 'basin' in opti_algo:
+            if init_guess is None:
+                init_guess = []
+                for t in self._theta:
+                    init_guess.append(t)
+                for p in self._p:
+                    init_guess.append(p)
+            bnds = []
+            for i in range(0, self._k):
+                bnds.append((-5., +5.))
+            for i in range(0, self._k):
+                bnds.append((1., 2.))
+            bounds = BasinHoppingBounds(xmax=list(zip(*bnds))[1], xmin=list(zip(*bnds))[0])
+            step = BasinHoppingStep()
+            minimizer_kwargs = dict(method='SLSQP', bounds=bnds, options={'disp': False, 'maxiter': 5e3}, tol=1e-4)
+            timer.tic()
+            res = basinhopping(self._calc_likelihood_opti_exp, init_guess, minimizer_kwargs=minimizer_kwargs,
+                               accept_test=bounds, take_step=step, niter=1000, niter_success=100)
+            timer.toc(print_it=True)
+        elif 'grid' in opti_algo:
+            skipper = LikeliOptimizer(debug=True)
+            timer.tic()
+            res = skipper.find(self._calc_likelihood_opti_exp, self._k)
+            timer.toc(print_it=True)
+        else:
+            raise Exception('ERROR: unknown optimizer selected')
+        exps = res.x[0:self._k]
+        thetas = []
+        for e in exps:
+            thetas.append(10. ** e)
+        if record_data:
+            print('Kriging Likelihood optimization evaluations: {:d}'.format(len(self.records)))
+        self.update_param(thetas, res.x[self._k:])
+
+    def predict(self, x_pred):
+        """
+        predicts a value from the surrogate model (reference: kriging.py:206-220)
+        :param x_pred: vector of input values (anything indexable with k entries)
+        :return: result value (numpy float64 scalar, usable as a scipy objective)
+        """
+        xq = np.array([[x_pred[i] for i in range(self._k)]], dtype=np.float64)
+        return self.predict_batch(xq)[0]
+
+    # ------------------------------------------------------------------ batched entry points (additive)
+    def likelihood_batch(self, log10_theta, p, return_best=False):
+        """nll for every row of an explicit candidate list: log10_theta[C,k], p[C,k] -> nll[C].
+        Replaces a loop of _calc_likelihood_opti_exp calls (kriging.py:130-141)."""
+        L = _cabi.lib()
+        d = self._dev()
+        e = np.atleast_2d(np.asarray(log10_theta, dtype=np.float64))
+        q = np.atleast_2d(np.asarray(p, dtype=np.float64))
+        if e.shape != q.shape or e.shape[1] != self._k:
+            raise ValueError('candidate tables must both be (C, k)')
+        C = e.shape[0]
+        if C == 0:
+            return (np.empty(0), float('inf'), -1) if return_best else np.empty(0)
+        theta = device.to_dev(np.power(10., e))  # 10.**e, vectorised
+        pd = device.to_dev(q)
+        nll = device.empty(C)
+        bv, bi = device.empty(1), device.empty(1, dtype=_int64())
+        _cabi.check(L.sm_krig_nll_batch(device.ptr(d['X']), device.ptr(d['y']), self._n, self._k, device.ptr(theta),
+                                        device.ptr(pd), C, 0, device.ptr(nll), device.ptr(bv), device.ptr(bi),
+                                        device.stream()))
+        out = nll.cpu().numpy()
+        nanrow = np.isnan(e).any(axis=1) | np.isnan(q).any(axis=1)
+        out[nanrow] = np.nan  # NaN parameters -> NaN (kriging.py:131-132)
+        if return_best:
+            return out, float(bv.item()), int(bi.item())
+        return out
+
+    def likelihood_grid(self, theta_sections=8, p_sections=5, c_begin=0, c_count=None, return_nll=True):
+        """nll over candidates [c_begin, c_begin + c_count) of LikeliOptimizer.generate_grid's enumeration
+        (likeli_optimizer.py:50-97) on THIS device.  Returns (best_val, best_idx, nll or None);
+        best_idx is the global flat index of the first strict minimum, -1 if nothing is finite."""
+        L = _cabi.lib()
+        d = self._dev()
+        T, P = int(theta_sections), int(p_sections)
+        total = (T ** self._k) * (P ** self._k)
+        c_count = total - c_begin if c_count is None else int(c_count)
+        th_axis, p_axis = grid_axes(T, P)
+        th_lin = device.to_dev(np.array([10.**e for e in th_axis]))  # scalar pow, like kriging.py:135-136
+        pa = device.to_dev(p_axis)
+        nll = device.empty(c_count) if return_nll else None
+        bv, bi = device.empty(1), device.empty(1, dtype=_int64())
+        _cabi.check(L.sm_krig_nll_grid(device.ptr(d['X']), device.ptr(d['y']), self._n, self._k, device.ptr(th_lin), T,
+                                       device.ptr(pa), P, int(c_begin), c_count, device.ptr(nll), device.ptr(bv),
+                                       device.ptr(bi), device.stream()))
+        return float(bv.item()), int(bi.item()), nll
+
+    def grid_search(self, theta_sections=8, p_sections=5, distributed=None, return_nll=False):
+        """The grid stage of LikeliOptimizer.find on the GPU(s).  With torch.distributed initialised the
+        candidate range is sharded contiguously over the ranks and only the (nll, index) pairs cross
+        NCCL; every rank returns the same (best_param, best_idx[, local nll])."""
+        T, P = int(theta_sections), int(p_sections)
+        total = (T ** self._k) * (P ** self._k)
+        rank, world = dist.rank_world(distributed)
+        lo, hi = dist.shard_range(total, rank, world)
+        bv, bi, nll = self.likelihood_grid(T, P, lo, hi - lo, return_nll=return_nll)
+        if world > 1:
+            bv, bi = dist.global_first_min(bv, bi)
+        param = None if bi < 0 else grid_param(self._k, T, P, bi)
+        if return_nll:
+            return param, bi, nll.cpu().numpy()
+        return param, bi
+
+    def predict_batch(self, x_query, return_mse=False):
+        """Mean (and ordinary-Kriging MSE) at many query points: Xq[Nq,k] -> y[Nq] (, mse[Nq]).
+        Replaces a Python loop over Kriging.predict (kriging.py:206-220)."""
+        if self._fit is None:  # the reference predicts with whatever update_param left behind
+            raise _cabi.SurrogateB200Error('predict before update_param / train: no fitted state')
+        xq = np.asarray(x_query, dtype=np.float64)
+        if xq.ndim == 1:
+            xq = xq.reshape(-1, self._k)
+        y, mse = self.predict_device(device.to_dev(xq), return_mse)
+        if return_mse:
+            return y.cpu().numpy(), mse.cpu().numpy()
+        return y.cpu().numpy()
+
+    def predict_device(self, xq_dev, return_mse=False):
+        """predict_batch on a device tensor Xq[Nq,k]; results stay on the device (no sync)."""
+        L = _cabi.lib()
+        d, f = self._dev(), self._fit
+        nq = xq_dev.shape[0]
+        y = device.empty(nq)
+        mse = device.empty(nq) if return_mse else None
+        if not f['ok']:
+            y.fill_(float('nan'))
+            if mse is not None:
+                mse.fill_(float('nan'))
+            return y, mse
+        _cabi.check(L.sm_krig_predict(device.ptr(d['X']), self._n, self._k, device.ptr(f['theta']), device.ptr(f['p']),
+                                      device.ptr(f['w']), f['mu'], f['sigma2'], device.ptr(f['Mop']),
+                                      device.ptr(f['b']), device.ptr(f['rres']), device.ptr(xq_dev), nq,
+                                      device.ptr(y), device.ptr(mse), device.stream()))
+        return y, mse
+
+    # ------------------------------------------------------------------ likelihood surface plots
+    def plot_theta_likelihood_r2(self, ax=None, pgf=False, opti_path=[]):
+        """colormap of the likelihood over theta1, theta2 (reference: kriging.py:222-252); the 50 x 50
+        sweep is one batched launch instead of 2500 update_param calls."""
+        if self._k != 2:
+            print('ERROR: plot_theta_likelihood_R2 only works with exactly 2 inputs')
+            return
+        from myutils.plot_helper import PlotHelper
+        thetas = np.logspace(-5, 5, num=50)
+        e1, e2 = np.meshgrid(np.log10(thetas), np.log10(thetas), indexing='ij')
+        cand_e = np.stack([e1.ravel(), e2.ravel()], axis=1)
+        cand_p = np.tile(self._p, (cand_e.shape[0], 1))
+        likely_thet = self.likelihood_batch(cand_e, cand_p).reshape(50, 50).T
+        plt_theta = PlotHelper([r'$\theta_{1}$', r'$\theta_{2}$'], fancy=False, ax=ax, pgf=pgf)
+        plt_theta.ax.set_xscale('log')
+        plt_theta.ax.set_yscale('log')
+        pcol = plt_theta.ax.pcolor(thetas, thetas, likely_thet, cmap='YlOrRd_r')
+        if len(opti_path) > 0:
+            plt_theta.ax.plot(10**opti_path[:, 0], 10**opti_path[:, 1], '+', color='white', markeredgewidth=0.5,
+                              markersize=5, label='Optimierer-Pfad')
+        plt_theta.ax.plot(self._theta[0], self._theta[1], 'x', color='black', label='Minimum', markersize=8,
+                          markeredgewidth=1.5)
+        plt_theta.finalize(width=6, height=5, legendLoc=4, show_legend=False)
+        return pcol
+
+    def plot_p_likelihood_r2(self, ax=None, pgf=False, opti_path=[]):
+        """colormap of the likelihood over p1, p2 (reference: kriging.py:254-282)"""
+        if self._k != 2:
+            print('ERROR: plot_p_likelihood_R2 only works with exactly 2 inputs')
+            return
+        from myutils.plot_helper import PlotHelper
+        ps = np.linspace(1., 2., num=50)
+        p1, p2 = np.meshgrid(ps, ps, indexing='ij')
+        cand_p = np.stack([p1.ravel(), p2.ravel()], axis=1)
+        cand_e = np.tile(np.log10(self._theta), (cand_p.shape[0], 1))
+        likely_p = self.likelihood_batch(cand_e, cand_p).reshape(50, 50).T
+        plt_P = PlotHelper(['$p_{1}$', '$p_{2}$'], fancy=False, ax=ax, pgf=pgf)
+        pcol = plt_P.ax.pcolor(ps, ps, likely_p, cmap='YlOrRd_r')
+        if len(opti_path) > 0:
+            plt_P.ax.plot(opti_path[:, 0], opti_path[:, 1], '+', color='white', markeredgewidth=0.5, markersize=5,
+                          label='Optimierer-Pfad')
+        plt_P.ax.plot(self._p[0], self._p[1], 'x', color='k', label='Minimum', markersize=8, markeredgewidth=1.5)
+        plt_P.finalize(width=6, height=5, legendLoc=4, show_legend=False)
+        return pcol
+
+    def plot_likelihoods(self, fancy=False, pgf=False, opti_path=[]):
+        """both colormaps side by side (reference: kriging.py:284-327)"""
+        if self._k != 2:
+            print('ERROR: plot_p_likelihood_R2 only works with exactly 2 inputs')
+            return
+        from myutils.plot_helper import PlotHelper
+        path_p, path_theta = [], []
+        if len(opti_path) > 0:
+            path_theta = np.array([opti_path[:, 0], opti_path[:, 1]]).T
+            path_p = np.array([opti_path[:, 2], opti_path[:, 3]]).T
+        plt_like = PlotHelper([], fancy=fancy, pgf=pgf)
+        import matplotlib.pyplot as plt
+        plt_like.fig = plt.figure()
+        ax1 = plt_like.fig.add_subplot(121)
+        ax2 = plt_like.fig.add_subplot(122)
+        pcol1 = self.plot_p_likelihood_r2(ax=ax1, pgf=pgf, opti_path=path_p)
+        pcol2 = self.plot_theta_likelihood_r2(ax=ax2, pgf=pgf, opti_path=path_theta)
+        like_min = min(pcol1.get_array().min(), pcol2.get_array().min())
+        like_max = max(pcol1.get_array().max(), pcol2.get_array().max())
+        pcol1.set_clim(like_min, like_max)
+        pcol2.set_clim(like_min, like_max)
+        plt_like.fig.set_size_inches(6, 3)
+        plt_like.fig.colorbar(pcol2)
+        return plt_like
+
+    def get_p(self):
+        return self._p
+
+    def get_theta(self):
+        return self._theta
+
+
+def _int64():
+    import torch
+    return torch.int64
+
+
+def grid_axes(theta_sections, p_sections):
+    """axes of LikeliOptimizer.generate_grid (likeli_optimizer.py:53-55): theta axis holds EXPONENTS"""
+    return np.linspace(-5, 5, num=theta_sections), np.linspace(1., 2., num=p_sections)
+
+
+def grid_param(k, theta_sections, p_sections, c):
+    """parameter vector [log10 theta_1..k, p_1..k] of flat grid index c (likeli_optimizer.py:59-86:
+    c = ip * T^k + it, dimension 0 the fastest digit)."""
+    th_axis, p_axis = grid_axes(theta_sections, p_sections)
+    T, P = theta_sections, p_sections
+    ip, it = divmod(int(c), T ** k)
+    param = [th_axis[(it // T ** d) % T] for d in range(k)]
+    param += [p_axis[(ip // P ** d) % P] for d in range(k)]
+    return param
+
+
+"""
+helper classes for basin hopping (reference: kriging.py:336-365)
+"""
+
+
+class BasinHoppingBounds(object):
+
+    def __init__(self, xmax=[5., 5., 2., 2.], xmin=[-5., -5., 1., 1.]):
+        self.xmax = np.array(xmax)
+        self.xmin = np.array(xmin)
+
+    def __call__(self, **kwargs):
+        x = kwargs["x_new"]
+        tmax = bool(np.all(x <= self.xmax))
+        tmin = bool(np.all(x >= self.xmin))
+        return tmax and tmin
+
+
+class BasinHoppingStep(object):
+
+    def __init__(self, stepsize=1.):
+        self.stepsize = stepsize
+
+    def __call__(self, x):
+        # the reference writes 10**U(-5,5) into the theta slots although the objective reads them as
+        # exponents (kriging.py:357-365); kept as is -- the bounds test rejects most such proposals
+        for i in range(0, len(x)):
+            if i < len(x) / 2:
+                x[i] = 10**np.random.uniform(-5, 5)
+            else:
+                x[i] = np.random.uniform(1., 2)
+        return x
