@@ -31,6 +31,21 @@ struct DevBuf {
     template <class T> T* as() { return static_cast<T*>(p); }
 };
 bool bad_nk(int n, int k) { return n < 1 || k < 1 || k > SM_KMAX; }
+
+// Scratch (tables, tile workspaces, partial minima) comes from the stream-ordered allocator.  Its default
+// pool returns memory to the driver at every synchronisation, which made the next call re-map it (tens of
+// ms); keep it cached instead.
+void keep_pool_cached() {
+    static thread_local int done_for = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done_for = dev;
+}
 }  // namespace
 
 namespace {
@@ -81,6 +96,7 @@ int sm_krig_nll_grid(const double* X, const double* y, int n, int k, const doubl
                      double* best_val, int64_t* best_idx, void* stream) {
     if (!X || !y || !theta_axis || !p_axis || bad_nk(n, k) || T < 1 || P < 1 || c_begin < 0 || c_count < 0)
         return SM_E_BADARG;
+    keep_pool_cached();
     cudaStream_t st = (cudaStream_t)stream;
     Launches L;
     const int npad = sm_krig_npad(n);
@@ -109,6 +125,7 @@ int sm_krig_nll_batch(const double* X, const double* y, int n, int k, const doub
                       int64_t C, int64_t idx_base, double* nll_out, double* best_val, int64_t* best_idx,
                       void* stream) {
     if (!X || !y || !theta || !p || bad_nk(n, k) || C < 0) return SM_E_BADARG;
+    keep_pool_cached();
     cudaStream_t st = (cudaStream_t)stream;
     Launches L;
     const int npad = sm_krig_npad(n);
@@ -136,6 +153,7 @@ int sm_krig_nll_batch(const double* X, const double* y, int n, int k, const doub
 int sm_krig_fit(const double* X, const double* y, int n, int k, const double* theta, const double* p,
                 double* scalars, double* w, double* b, double* rres, double* Mop, double* R, void* stream) {
     if (!X || !y || !theta || !p || !scalars || !w || !b || !rres || !Mop || bad_nk(n, k)) return SM_E_BADARG;
+    keep_pool_cached();
     Launches L;
     FitOut out{scalars, w, b, rres, Mop, R};
     SM_TRY(launch_krig_fit(X, y, n, k, theta, p, out, (cudaStream_t)stream, &L.n));
@@ -146,6 +164,7 @@ int sm_krig_predict(const double* X, int n, int k, const double* theta, const do
                     double mu, double sigma2, const double* Mop, const double* b, const double* rres,
                     const double* Xq, int64_t Nq, double* y_out, double* mse_out, void* stream) {
     if (!X || !theta || !p || !w || !Xq || !y_out || bad_nk(n, k) || Nq < 0) return SM_E_BADARG;
+    keep_pool_cached();
     if (mse_out && (!Mop || !b || !rres)) return SM_E_BADARG;
     Launches L;
     PredictArgs a{};
@@ -160,6 +179,7 @@ int sm_krig_predict(const double* X, int n, int k, const double* theta, const do
 int sm_rbf_fit(const double* X, const double* y, int n, int k, int kind, double a, double* coeff, int* info,
                void* stream) {
     if (!X || !y || !coeff || !info || bad_nk(n, k) || kind < 0 || kind > 4) return SM_E_BADARG;
+    keep_pool_cached();
     Launches L;
     SM_TRY(launch_rbf_fit(X, y, n, k, kind, a, coeff, info, (cudaStream_t)stream, &L.n));
     return 0;
@@ -168,6 +188,7 @@ int sm_rbf_fit(const double* X, const double* y, int n, int k, int kind, double 
 int sm_rbf_predict(const double* X, int n, int k, int kind, double a, const double* coeff, const double* Xq,
                    int64_t Nq, double* y_out, void* stream) {
     if (!X || !coeff || !Xq || !y_out || bad_nk(n, k) || kind < 0 || kind > 4 || Nq < 0) return SM_E_BADARG;
+    keep_pool_cached();
     Launches L;
     SM_TRY(launch_rbf_predict(X, n, k, kind, a, coeff, Xq, Nq, y_out, (cudaStream_t)stream, &L.n));
     return 0;

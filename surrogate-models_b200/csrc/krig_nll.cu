@@ -29,7 +29,9 @@ __global__ void dtab_kernel(const double* __restrict__ X, int n, int k, int npad
         const int i = (int)((t / npad) % npad);
         const int dq = (int)(t / per);
         const int q = dq % P, d = dq / P;
-        double v = 0.0;
+        // padding (i or j >= n): identity -- off-diagonal DBL_MAX (theta * D overflows, exp(-s) = 0),
+        // diagonal 0 (exp(-0) = 1), so the kernels need no bounds test on the entries
+        double v = (i == j) ? 0.0 : 1.7976931348623157e308;
         if (i < n && j < n) {
             const double dx = fabs(X[(size_t)i * k + d] - X[(size_t)j * k + d]);
             v = pow(dx, p_axis[q]);  // abs(dx) ** p  (kriging.py:75); 0 ** p = 0
@@ -45,7 +47,7 @@ __global__ void logtab_kernel(const double* __restrict__ X, int n, int k, int np
         const int j = (int)(t % npad);
         const int i = (int)((t / npad) % npad);
         const int d = (int)(t / per);
-        double v = -INFINITY;
+        double v = (i == j) ? -INFINITY : 709.0;  // padding: identity (see dtab_kernel)
         if (i < n && j < n) v = log(fabs(X[(size_t)i * k + d] - X[(size_t)j * k + d]));  // ln 0 = -inf
         LG[t] = v;
     }
@@ -323,6 +325,13 @@ cudaError_t launch_nll(NllArgs a, int mode, cudaStream_t st, long long* launches
     const NllPlan pl = plan_nll(a.n);
     a.npad = pl.npad;
     if (a.C <= 0) return cudaSuccess;
+    {  // n <= 64, k <= 4: specialised warp-per-candidate kernel (krig_nll_small.cu)
+        const cudaError_t es = launch_nll_small(a, mode, st);
+        if (es != cudaErrorNotSupported) {
+            if (launches) *launches += 1;
+            return es;
+        }
+    }
     long long ctas_needed = (a.C + pl.cands_per_cta - 1) / pl.cands_per_cta;
     long long grid = (long long)g_sms * pl.ctas_per_sm;
     if (grid > ctas_needed) grid = ctas_needed;

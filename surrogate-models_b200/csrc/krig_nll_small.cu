@@ -1,0 +1,360 @@
+// Small-n (n <= 64) batched likelihood kernel: ONE WARP PER CANDIDATE, everything in shared memory and
+// registers, no block-level barrier in the candidate loop.  Same algorithm and results contract as the
+// generic engine (tile_chol.cuh / krig_nll.cu: left-looking 8x8-tile Cholesky on DMMA, fused correlation
+// build, solves of y and 1), restructured after the first ncu profile (profiles/r01_nll_generic_ncu.md):
+//   * strictly-lower tiles only (the diagonal tile lives in registers), right-hand sides stored as 2 rows
+//     -> 15.9 KB per candidate at n = 64 -> 14 resident warps per SM instead of 9;
+//   * tile loops are compile-time shaped (NTM), offsets are 32-bit, parameters sit in registers;
+//   * the correlation entries of a block column are produced pairwise with a branch-free table-driven exp
+//     (fastmath.cuh) so independent evaluations interleave;
+//   * accumulator->operand layout changes go through a bank-conflict-free swizzled tile layout.
+// Reference semantics: mylibs/kriging.py:53-116,130-141 per candidate; enumeration of
+// mylibs/likeli_optimizer.py:50-97 in grid mode.
+#include "fastmath.cuh"
+#include "tile_chol.cuh"
+#include "kernels.h"
+
+namespace smb {
+
+// swizzled operand order: 16-byte chunk index XOR ((row >> 1) & 1): accumulator-fragment stores (2 x STS.64
+// per lane) then hit every bank exactly twice, operand loads stay one conflict-free LDS.128 per lane.
+// The per-lane offsets are computed once per thread (LaneOff) -- recomputing them per access was ~9% of
+// all executed instructions in the first profile.
+struct LaneOff {
+    int ld;        // operand pair of this lane: doubles [ld, ld+1]
+    int st0, st1;  // accumulator elements (r, 2q), (r, 2q+1)
+    __device__ __forceinline__ explicit LaneOff(int lane) {
+        const int r = lane >> 2, q = lane & 3, s = (r >> 1) & 1, ch = (2 * q) & 3;
+        ld = 2 * (lane ^ s);
+        st0 = 8 * r + 2 * (ch ^ s) + (q >> 1);
+        st1 = 8 * r + 2 * ((ch + 1) ^ s) + (q >> 1);
+    }
+};
+__device__ __forceinline__ double2 ld_frag_sw(const double* tile, const LaneOff& o) {
+    return *reinterpret_cast<const double2*>(tile + o.ld);
+}
+__device__ __forceinline__ void st_acc_sw(double* tile, const LaneOff& o, double c0, double c1) {
+    tile[o.st0] = c0;
+    tile[o.st1] = c1;
+}
+
+template <int KD>
+struct SmallParams {
+    double th[KD];
+    const double* tab[KD];  // grid: D table of (d, q_d); list: log table of d
+    double pw[KD];          // list mode only
+};
+
+// entries (i, j), (i, j+1) of R for this lane; tables are padded so that no bounds test is needed
+// (krig_nll.cu: off-diagonal padding gives exp(-huge) = 0, diagonal padding gives exp(-0) = 1)
+template <int KD, int MODE>
+__device__ __forceinline__ void small_entry(const SmallParams<KD>& P, int off, const double* etab, double& v0, double& v1) {
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int d = 0; d < KD; ++d) {
+        const double2 t = *reinterpret_cast<const double2*>(P.tab[d] + off);
+        double e0 = t.x, e1 = t.y;
+        if (MODE == 1) {
+            e0 = exp_fast<true>(P.pw[d] * t.x, etab);
+            e1 = exp_fast<true>(P.pw[d] * t.y, etab);
+        }
+        s0 = __dadd_rn(s0, __dmul_rn(P.th[d], e0));
+        s1 = __dadd_rn(s1, __dmul_rn(P.th[d], e1));
+    }
+    v0 = exp_fast<false>(-s0, etab);
+    v1 = exp_fast<false>(-s1, etab);
+}
+
+// 8x8 Cholesky + inverse of the diagonal tile.  In: the tile in accumulator layout (c0, c1).  Out: W = L^-1
+// written to `wt` in swizzled operand order (ready to be the B operand of the panel solve); returns the
+// product of the 8 pivots in `tp`; false on a pivot <= 0 / NaN.
+// Broadcasts go through two 64-double shared scratch tiles instead of warp shuffles (a 64-bit shuffle is
+// 2 SHFL + register packing; the shuffle version was 29% of all executed instructions):
+//   ts[c * 8 + r]  column-major working copy of the tile: step j reads the pivot, its own row's entry of
+//                  column j and the two entries matching its columns; only column j+1 is written back.
+//   wt             row j of W is final (scaled) after step j and is stored straight into operand order;
+//                  the rank-1 update of the rows below runs one step late so ONE __syncwarp per step suffices.
+// Entries outside the lower triangle pick up meaningless (finite) updates and are never read.
+__device__ __forceinline__ bool diag_factor(double c0, double c1, double* __restrict__ ts, double* __restrict__ wt,
+                                            double& tp, int lane) {
+    const int r = lane >> 2, q = lane & 3;
+    const int s = (r >> 1) & 1;
+    bool ok = true;
+    double w0 = (r == 2 * q) ? 1.0 : 0.0, w1 = (r == 2 * q + 1) ? 1.0 : 0.0;
+    ts[(2 * q) * 8 + r] = c0;
+    ts[(2 * q + 1) * 8 + r] = c1;
+    tp = 1.0;
+    double lrw_prev = 0.0;
+    // operand-order positions of W[row][2q], W[row][2q+1] for row = r: used for the store (row = r == j)
+    // and, with row = j, for the delayed read
+    const int chq = (2 * q) & 3;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        __syncwarp();
+        if (j > 0) {  // delayed W update with row j-1 (final since the previous step)
+            const int sj = ((j - 1) >> 1) & 1;
+            const double wj0 = wt[8 * (j - 1) + 2 * (chq ^ sj) + (q >> 1)];
+            const double wj1 = wt[8 * (j - 1) + 2 * ((chq + 1) ^ sj) + (q >> 1)];
+            if (r > j - 1) {
+                w0 = fma(-lrw_prev, wj0, w0);
+                w1 = fma(-lrw_prev, wj1, w1);
+            }
+        }
+        const double d = ts[j * 8 + j];
+        const double vr = ts[j * 8 + r];
+        const double2 vc = *reinterpret_cast<const double2*>(ts + j * 8 + 2 * q);
+        ok = ok && (d > 0.0);
+        tp *= d;
+        const double inv = rsqrt(d);
+        const double t = vr * (inv * inv);
+        c0 = fma(-t, vc.x, c0);
+        c1 = fma(-t, vc.y, c1);
+        lrw_prev = vr * inv;  // L[r][j]
+        if (r == j) {         // row j of W is final: scale and publish in operand order
+            wt[8 * r + 2 * (chq ^ s) + (q >> 1)] = w0 * inv;
+            wt[8 * r + 2 * ((chq + 1) ^ s) + (q >> 1)] = w1 * inv;
+        }
+        if (j < 7 && q == ((j + 1) >> 1)) ts[(j + 1) * 8 + r] = ((j + 1) & 1) ? c1 : c0;
+    }
+    __syncwarp();
+    return ok;
+}
+
+// shared memory per warp (doubles): strictly-lower tiles | rhs rows (2 x npad) | W tile | diagonal working tile
+__host__ __device__ inline int small_warp_doubles(int ntm) { return ntm * (ntm - 1) / 2 * 64 + ntm * 16 + 128; }
+
+template <int NTM, int KD, int MODE>
+__global__ void __launch_bounds__(32 * 8, 2) krig_nll_small_kernel(const NllArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int r = lane >> 2, q = lane & 3;
+    const int NT = a.npad >> 3, npad = a.npad;
+    double* etab = smem;                 // [32]
+    double* y_s = etab + EXP_TAB;        // [8 NTM]
+    double* mine = y_s + 8 * NTM + (size_t)wid * small_warp_doubles(NTM);
+    double* tiles = mine;                                   // tile (I, K), K < I, at (I (I-1)/2 + K) * 64
+    double* rhs_s = tiles + NTM * (NTM - 1) / 2 * 64;       // [Jt][2][8]: rows y^T / 1^T
+    double* wscr = rhs_s + NTM * 16;                        // [64] W_J in operand order
+    double* dscr = wscr + 64;                               // [64] diagonal tile, column-major working copy
+    const LaneOff lo(lane);
+    exp_table_init(etab, threadIdx.x, blockDim.x);
+    for (int j = threadIdx.x; j < 8 * NTM; j += blockDim.x) y_s[j] = (j < a.n) ? a.y[j] : 0.0;
+    __syncthreads();
+
+    const int lane_off = r * npad + 2 * q;  // this lane's entry offset inside a tile's table window
+    const long long per = (long long)npad * npad;
+    const long long first = (long long)blockIdx.x * nwarps + wid, stride = (long long)gridDim.x * nwarps;
+
+    for (long long c = first; c < a.C; c += stride) {
+        // ---------------------------------------------------------------- candidate parameters
+        SmallParams<KD> P;
+        if (MODE == 0) {
+            long long tk = 1;
+#pragma unroll
+            for (int d = 0; d < KD; ++d) tk *= a.T;
+            const long long cg = a.c_begin + c;
+            long long it = cg % tk, ip = cg / tk;
+#pragma unroll
+            for (int d = 0; d < KD; ++d) {
+                P.th[d] = a.theta_axis[it % a.T];
+                P.tab[d] = a.dtab + ((long long)d * a.P + (ip % a.P)) * per;
+                it /= a.T;
+                ip /= a.P;
+            }
+        } else {
+#pragma unroll
+            for (int d = 0; d < KD; ++d) {
+                P.th[d] = a.theta[c * KD + d];
+                P.pw[d] = a.p[c * KD + d];
+                P.tab[d] = a.logtab + d * per;
+            }
+        }
+        double prod = 1.0;
+        bool ok = true;
+
+        for (int J = 0; J < NT; ++J) {
+            const int cnt = NT - J;  // matrix tiles in this block column: I = J + g, g < cnt (g = 0: diagonal)
+            // ------------------------------------------------------------ U: C = A - sum_K L_IK L_JK^T
+            double acc[NTM][2], accr[2] = {0.0, 0.0};
+#pragma unroll
+            for (int g = 0; g < NTM; ++g) acc[g][0] = acc[g][1] = 0.0;
+            const double* rowJ = tiles + J * (J - 1) / 2 * 64;
+            for (int K = 0; K < J; ++K) {
+                const double2 b = ld_frag_sw(rowJ + K * 64, lo);
+                dmma(acc[0][0], acc[0][1], b.x, b.x);
+                dmma(acc[0][0], acc[0][1], b.y, b.y);
+#pragma unroll
+                for (int g = 1; g < NTM; ++g) {
+                    if (g < cnt) {
+                        const int I = J + g;
+                        const double2 av = ld_frag_sw(tiles + (I * (I - 1) / 2 + K) * 64, lo);
+                        dmma(acc[g][0], acc[g][1], av.x, b.x);
+                        dmma(acc[g][0], acc[g][1], av.y, b.y);
+                    }
+                }
+                // right-hand sides: rows 0 / 1 of an otherwise zero tile
+                const double a0 = (r < 2) ? rhs_s[K * 16 + r * 8 + q] : 0.0;
+                const double a1 = (r < 2) ? rhs_s[K * 16 + r * 8 + q + 4] : 0.0;
+                dmma(accr[0], accr[1], a0, b.x);
+                dmma(accr[0], accr[1], a1, b.y);
+            }
+            // correlation entries of this block column, two tiles (4 exp per lane) at a time
+            const int col_off = 8 * J + lane_off;
+#pragma unroll
+            for (int g = 0; g < NTM; g += 2) {
+                if (g < cnt) {
+                    double v0, v1, u0, u1;
+                    // second tile of the pair: clamped to a valid row block when the column has an odd
+                    // count (computed, never used) so both evaluations share one basic block
+                    const int g1 = (g + 1 < cnt) ? g + 1 : g;
+                    small_entry<KD, MODE>(P, (J + g) * 8 * npad + col_off, etab, v0, v1);
+                    small_entry<KD, MODE>(P, (J + g1) * 8 * npad + col_off, etab, u0, u1);
+                    acc[g][0] = v0 - acc[g][0];
+                    acc[g][1] = v1 - acc[g][1];
+                    if (g + 1 < NTM) {
+                        acc[g + 1][0] = u0 - acc[g + 1][0];
+                        acc[g + 1][1] = u1 - acc[g + 1][1];
+                    }
+                }
+            }
+            {
+                const int j0 = 8 * J + 2 * q;
+                const double y0 = (r == 0) ? y_s[j0] : ((r == 1 && j0 < a.n) ? 1.0 : 0.0);
+                const double y1 = (r == 0) ? y_s[j0 + 1] : ((r == 1 && j0 + 1 < a.n) ? 1.0 : 0.0);
+                accr[0] = y0 - accr[0];
+                accr[1] = y1 - accr[1];
+            }
+            // ------------------------------------------------------------ D: diagonal tile in registers
+            double tp;
+            ok = diag_factor(acc[0][0], acc[0][1], dscr, wscr, tp, lane) && ok;
+            if (!ok) break;  // warp-uniform
+            if (lane == J) prod = tp;  // NT <= 8: lane J keeps the pivot product of tile J
+            // park the un-normalised panel tiles in their final slots (accumulator -> operand layout)
+#pragma unroll
+            for (int g = 1; g < NTM; ++g) {
+                if (g < cnt) {
+                    const int I = J + g;
+                    st_acc_sw(tiles + (I * (I - 1) / 2 + J) * 64, lo, acc[g][0], acc[g][1]);
+                }
+            }
+            if (r < 2) {
+                rhs_s[J * 16 + r * 8 + 2 * q] = accr[0];
+                rhs_s[J * 16 + r * 8 + 2 * q + 1] = accr[1];
+            }
+            __syncwarp();
+            // ------------------------------------------------------------ T: L_IJ = C_IJ W^T
+            const double2 wf = ld_frag_sw(wscr, lo);
+            double t[NTM][2], tr[2] = {0.0, 0.0};
+#pragma unroll
+            for (int g = 1; g < NTM; ++g) {
+                if (g < cnt) {
+                    const int I = J + g;
+                    const double2 av = ld_frag_sw(tiles + (I * (I - 1) / 2 + J) * 64, lo);
+                    t[g][0] = t[g][1] = 0.0;
+                    dmma(t[g][0], t[g][1], av.x, wf.x);
+                    dmma(t[g][0], t[g][1], av.y, wf.y);
+                }
+            }
+            {
+                const double a0 = (r < 2) ? rhs_s[J * 16 + r * 8 + q] : 0.0;
+                const double a1 = (r < 2) ? rhs_s[J * 16 + r * 8 + q + 4] : 0.0;
+                dmma(tr[0], tr[1], a0, wf.x);
+                dmma(tr[0], tr[1], a1, wf.y);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int g = 1; g < NTM; ++g) {
+                if (g < cnt) {
+                    const int I = J + g;
+                    st_acc_sw(tiles + (I * (I - 1) / 2 + J) * 64, lo, t[g][0], t[g][1]);
+                }
+            }
+            if (r < 2) {
+                rhs_s[J * 16 + r * 8 + 2 * q] = tr[0];
+                rhs_s[J * 16 + r * 8 + 2 * q + 1] = tr[1];
+            }
+            __syncwarp();
+        }
+        // ---------------------------------------------------------------- epilogue
+        double nll = INFINITY;
+        if (ok) {
+            const double logdet_half = 0.5 * warp_sum((lane < NT) ? log(prod) : 0.0);
+            double sab = 0.0, sbb = 0.0;
+            for (int j = lane; j < a.n; j += 32) {
+                const double av = rhs_s[(j >> 3) * 16 + (j & 7)], bv = rhs_s[(j >> 3) * 16 + 8 + (j & 7)];
+                sab = fma(av, bv, sab);
+                sbb = fma(bv, bv, sbb);
+            }
+            sab = warp_sum(sab);
+            sbb = warp_sum(sbb);
+            const double mu = sab / sbb;
+            double srr = 0.0;
+            for (int j = lane; j < a.n; j += 32) {
+                const double rj = fma(-mu, rhs_s[(j >> 3) * 16 + 8 + (j & 7)], rhs_s[(j >> 3) * 16 + (j & 7)]);
+                srr = fma(rj, rj, srr);
+            }
+            srr = warp_sum(srr);
+            nll = 0.5 * a.n * log(srr / a.n) + logdet_half;
+        }
+        if (lane == 0) a.nll_out[c] = nll;
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------ launcher
+template <int NTM, int KD>
+static cudaError_t launch_small_t(const NllArgs& a, int mode, cudaStream_t st) {
+    const size_t per_sm = 228 * 1024, reserved = 1024;
+    const size_t fixed = (EXP_TAB + 8 * NTM) * 8, per_warp = (size_t)small_warp_doubles(NTM) * 8;
+    int best_w = 0, best_wpc = 1;
+    for (int wpc = 1; wpc <= 8; ++wpc) {  // warps (candidates) per CTA maximising resident warps per SM
+        const size_t sm = fixed + wpc * per_warp;
+        if (sm > smem_optin()) break;
+        int ctas = (int)(per_sm / (sm + reserved));
+        if (ctas > 32) ctas = 32;
+        int w = ctas * wpc;
+        if (w > 16) w = 16;  // register file: 16 warps x 128 registers
+        if (w > best_w) { best_w = w; best_wpc = wpc; }
+    }
+    const size_t smem = fixed + best_wpc * per_warp;
+    int ctas_per_sm = (int)(per_sm / (smem + reserved));
+    if (ctas_per_sm * best_wpc > 16) ctas_per_sm = 16 / best_wpc;
+    long long grid = (long long)sm_count() * ctas_per_sm;
+    const long long need = (a.C + best_wpc - 1) / best_wpc;
+    if (grid > need) grid = need;
+    cudaError_t e;
+    if (mode == 0) {
+        e = cudaFuncSetAttribute(krig_nll_small_kernel<NTM, KD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        krig_nll_small_kernel<NTM, KD, 0><<<(int)grid, 32 * best_wpc, smem, st>>>(a);
+    } else {
+        e = cudaFuncSetAttribute(krig_nll_small_kernel<NTM, KD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        krig_nll_small_kernel<NTM, KD, 1><<<(int)grid, 32 * best_wpc, smem, st>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+template <int NTM>
+static cudaError_t launch_small_k(const NllArgs& a, int mode, cudaStream_t st) {
+    switch (a.k) {
+        case 1: return launch_small_t<NTM, 1>(a, mode, st);
+        case 2: return launch_small_t<NTM, 2>(a, mode, st);
+        case 3: return launch_small_t<NTM, 3>(a, mode, st);
+        case 4: return launch_small_t<NTM, 4>(a, mode, st);
+        default: return cudaErrorNotSupported;
+    }
+}
+
+// n <= 64 and k <= 4: the specialised kernel; anything else returns cudaErrorNotSupported and the caller
+// uses the generic engine
+cudaError_t launch_nll_small(const NllArgs& a, int mode, cudaStream_t st) {
+    const int NT = a.npad / 8;
+    if (a.k > 4 || NT > 8 || a.C <= 0) return cudaErrorNotSupported;
+    if (NT <= 2) return launch_small_k<2>(a, mode, st);
+    if (NT <= 4) return launch_small_k<4>(a, mode, st);
+    if (NT <= 6) return launch_small_k<6>(a, mode, st);
+    return launch_small_k<8>(a, mode, st);
+}
+
+}  // namespace smb
