@@ -20,7 +20,8 @@ __host__ __device__ __forceinline__ int tile_pos(int r, int c) { return 8 * r + 
 
 // D(8x8) += A(8x4) * B(4x8); lane l holds A[l/4][l%4], B[l%4][l/4], D[l/4][2(l%4)], D[l/4][2(l%4)+1]
 __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+    // not volatile: a pure function of its operands, so ptxas may interleave independent accumulator chains
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 

@@ -46,17 +46,26 @@ struct SmallParams {
 };
 
 // entries (i, j), (i, j+1) of R for this lane; tables are padded so that no bounds test is needed
-// (krig_nll.cu: off-diagonal padding gives exp(-huge) = 0, diagonal padding gives exp(-0) = 1)
+// (krig_nll.cu: off-diagonal padding gives exp(-huge) = 0, diagonal padding gives exp(-0) = 1).
+// Split into the table load (issued early) and the evaluation.
+template <int KD>
+__device__ __forceinline__ void load_pair(const SmallParams<KD>& P, int off0, int off1, double2 (&t)[2][KD]) {
+#pragma unroll
+    for (int d = 0; d < KD; ++d) {
+        t[0][d] = *reinterpret_cast<const double2*>(P.tab[d] + off0);
+        t[1][d] = *reinterpret_cast<const double2*>(P.tab[d] + off1);
+    }
+}
 template <int KD, int MODE>
-__device__ __forceinline__ void small_entry(const SmallParams<KD>& P, int off, const double* etab, double& v0, double& v1) {
+__device__ __forceinline__ void eval_entry(const SmallParams<KD>& P, const double2 (&t)[KD], const double* etab,
+                                           double& v0, double& v1) {
     double s0 = 0.0, s1 = 0.0;
 #pragma unroll
     for (int d = 0; d < KD; ++d) {
-        const double2 t = *reinterpret_cast<const double2*>(P.tab[d] + off);
-        double e0 = t.x, e1 = t.y;
+        double e0 = t[d].x, e1 = t[d].y;
         if (MODE == 1) {
-            e0 = exp_fast<true>(P.pw[d] * t.x, etab);
-            e1 = exp_fast<true>(P.pw[d] * t.y, etab);
+            e0 = exp_fast<true>(P.pw[d] * e0, etab);
+            e1 = exp_fast<true>(P.pw[d] * e1, etab);
         }
         s0 = __dadd_rn(s0, __dmul_rn(P.th[d], e0));
         s1 = __dadd_rn(s1, __dmul_rn(P.th[d], e1));
@@ -124,7 +133,7 @@ __device__ __forceinline__ bool diag_factor(double c0, double c1, double* __rest
 __host__ __device__ inline int small_warp_doubles(int ntm) { return ntm * (ntm - 1) / 2 * 64 + ntm * 16 + 128; }
 
 template <int NTM, int KD, int MODE>
-__global__ void __launch_bounds__(32 * 8, 2) krig_nll_small_kernel(const NllArgs a) {
+__global__ void __launch_bounds__(256, 2) krig_nll_small_kernel(const NllArgs a) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int r = lane >> 2, q = lane & 3;
@@ -174,46 +183,84 @@ __global__ void __launch_bounds__(32 * 8, 2) krig_nll_small_kernel(const NllArgs
 
         for (int J = 0; J < NT; ++J) {
             const int cnt = NT - J;  // matrix tiles in this block column: I = J + g, g < cnt (g = 0: diagonal)
-            // ------------------------------------------------------------ U: C = A - sum_K L_IK L_JK^T
-            double acc[NTM][2], accr[2] = {0.0, 0.0};
-#pragma unroll
-            for (int g = 0; g < NTM; ++g) acc[g][0] = acc[g][1] = 0.0;
             const double* rowJ = tiles + J * (J - 1) / 2 * 64;
-            for (int K = 0; K < J; ++K) {
-                const double2 b = ld_frag_sw(rowJ + K * 64, lo);
-                dmma(acc[0][0], acc[0][1], b.x, b.x);
-                dmma(acc[0][0], acc[0][1], b.y, b.y);
-#pragma unroll
-                for (int g = 1; g < NTM; ++g) {
-                    if (g < cnt) {
-                        const int I = J + g;
-                        const double2 av = ld_frag_sw(tiles + (I * (I - 1) / 2 + K) * 64, lo);
-                        dmma(acc[g][0], acc[g][1], av.x, b.x);
-                        dmma(acc[g][0], acc[g][1], av.y, b.y);
-                    }
-                }
-                // right-hand sides: rows 0 / 1 of an otherwise zero tile
-                const double a0 = (r < 2) ? rhs_s[K * 16 + r * 8 + q] : 0.0;
-                const double a1 = (r < 2) ? rhs_s[K * 16 + r * 8 + q + 4] : 0.0;
-                dmma(accr[0], accr[1], a0, b.x);
-                dmma(accr[0], accr[1], a1, b.y);
-            }
-            // correlation entries of this block column, two tiles (4 exp per lane) at a time
             const int col_off = 8 * J + lane_off;
+            double dc0 = 0.0, dc1 = 0.0;         // diagonal tile (accumulator layout)
+            double accr[2] = {0.0, 0.0};         // right-hand-side rows
+            // ------------------------------------------------------------ U: C = A - sum_K L_IK L_JK^T
+            // the block column is processed in chunks of G = 4 tiles: 4-5 independent DMMA accumulator chains
+            // (the DMMA latency is 40 cycles, its issue interval 16) at half the registers of a full column;
+            // 2 x 7 warps per SM only fit with <= 128 registers per thread
 #pragma unroll
-            for (int g = 0; g < NTM; g += 2) {
-                if (g < cnt) {
+            for (int g0 = 0; g0 < NTM; g0 += 4) {
+                if (g0 < cnt) {  // warp-uniform
+                    double acc[4][2];
+#pragma unroll
+                    for (int gg = 0; gg < 4; ++gg) acc[gg][0] = acc[gg][1] = 0.0;
+                    // table entries of the chunk's first tile pair: in flight during the DMMA loop
+                    double2 tq[2][KD];
+                    load_pair<KD>(P, (J + g0) * 8 * npad + col_off, (J + (g0 + 1 < cnt ? g0 + 1 : g0)) * 8 * npad + col_off, tq);
+                    for (int K = 0; K < J; ++K) {
+                        // operands first (independent LDS), then every first k-half, then every second k-half
+                        const double2 b = ld_frag_sw(rowJ + K * 64, lo);
+                        double2 av[4];
+#pragma unroll
+                        for (int gg = 0; gg < 4; ++gg) {
+                            const int g = g0 + gg;
+                            av[gg] = b;  // g == 0: the diagonal tile, L_JK L_JK^T
+                            if (g > 0 && g < NTM && g < cnt) {
+                                const int I = J + g;
+                                av[gg] = ld_frag_sw(tiles + (I * (I - 1) / 2 + K) * 64, lo);
+                            }
+                        }
+                        double a0 = 0.0, a1 = 0.0;
+                        if (g0 == 0 && r < 2) {
+                            a0 = rhs_s[K * 16 + r * 8 + q];
+                            a1 = rhs_s[K * 16 + r * 8 + q + 4];
+                        }
+#pragma unroll
+                        for (int gg = 0; gg < 4; ++gg)
+                            if (g0 + gg < NTM && g0 + gg < cnt) dmma(acc[gg][0], acc[gg][1], av[gg].x, b.x);
+                        if (g0 == 0) dmma(accr[0], accr[1], a0, b.x);
+#pragma unroll
+                        for (int gg = 0; gg < 4; ++gg)
+                            if (g0 + gg < NTM && g0 + gg < cnt) dmma(acc[gg][0], acc[gg][1], av[gg].y, b.y);
+                        if (g0 == 0) dmma(accr[0], accr[1], a1, b.y);
+                    }
+                    // correlation entries, two tiles (4 exp per lane) at a time; the second pair's table
+                    // entries are requested before the first pair is evaluated
+                    double2 tn[2][KD];
+                    const bool second = (g0 + 2 < NTM) && (g0 + 2 < cnt);
+                    if (second) {
+                        const int g3 = (g0 + 3 < cnt) ? g0 + 3 : g0 + 2;
+                        load_pair<KD>(P, (J + g0 + 2) * 8 * npad + col_off, (J + g3) * 8 * npad + col_off, tn);
+                    }
                     double v0, v1, u0, u1;
-                    // second tile of the pair: clamped to a valid row block when the column has an odd
-                    // count (computed, never used) so both evaluations share one basic block
-                    const int g1 = (g + 1 < cnt) ? g + 1 : g;
-                    small_entry<KD, MODE>(P, (J + g) * 8 * npad + col_off, etab, v0, v1);
-                    small_entry<KD, MODE>(P, (J + g1) * 8 * npad + col_off, etab, u0, u1);
-                    acc[g][0] = v0 - acc[g][0];
-                    acc[g][1] = v1 - acc[g][1];
-                    if (g + 1 < NTM) {
-                        acc[g + 1][0] = u0 - acc[g + 1][0];
-                        acc[g + 1][1] = u1 - acc[g + 1][1];
+                    eval_entry<KD, MODE>(P, tq[0], etab, v0, v1);
+                    eval_entry<KD, MODE>(P, tq[1], etab, u0, u1);  // odd count: a repeat, never stored
+                    acc[0][0] = v0 - acc[0][0];
+                    acc[0][1] = v1 - acc[0][1];
+                    acc[1][0] = u0 - acc[1][0];
+                    acc[1][1] = u1 - acc[1][1];
+                    if (second) {
+                        eval_entry<KD, MODE>(P, tn[0], etab, v0, v1);
+                        eval_entry<KD, MODE>(P, tn[1], etab, u0, u1);
+                        acc[2][0] = v0 - acc[2][0];
+                        acc[2][1] = v1 - acc[2][1];
+                        acc[3][0] = u0 - acc[3][0];
+                        acc[3][1] = u1 - acc[3][1];
+                    }
+                    // park the un-normalised panel tiles in their final slots (accumulator -> operand layout)
+#pragma unroll
+                    for (int gg = 0; gg < 4; ++gg) {
+                        const int g = g0 + gg;
+                        if (g == 0) {
+                            dc0 = acc[0][0];
+                            dc1 = acc[0][1];
+                        } else if (g < NTM && g < cnt) {
+                            const int I = J + g;
+                            st_acc_sw(tiles + (I * (I - 1) / 2 + J) * 64, lo, acc[gg][0], acc[gg][1]);
+                        }
                     }
                 }
             }
@@ -221,57 +268,59 @@ __global__ void __launch_bounds__(32 * 8, 2) krig_nll_small_kernel(const NllArgs
                 const int j0 = 8 * J + 2 * q;
                 const double y0 = (r == 0) ? y_s[j0] : ((r == 1 && j0 < a.n) ? 1.0 : 0.0);
                 const double y1 = (r == 0) ? y_s[j0 + 1] : ((r == 1 && j0 + 1 < a.n) ? 1.0 : 0.0);
-                accr[0] = y0 - accr[0];
-                accr[1] = y1 - accr[1];
+                if (r < 2) {
+                    rhs_s[J * 16 + r * 8 + 2 * q] = y0 - accr[0];
+                    rhs_s[J * 16 + r * 8 + 2 * q + 1] = y1 - accr[1];
+                }
             }
-            // ------------------------------------------------------------ D: diagonal tile in registers
+            // ------------------------------------------------------------ D: diagonal tile
             double tp;
-            ok = diag_factor(acc[0][0], acc[0][1], dscr, wscr, tp, lane) && ok;
+            ok = diag_factor(dc0, dc1, dscr, wscr, tp, lane) && ok;  // ends with __syncwarp
             if (!ok) break;  // warp-uniform
             if (lane == J) prod = tp;  // NT <= 8: lane J keeps the pivot product of tile J
-            // park the un-normalised panel tiles in their final slots (accumulator -> operand layout)
-#pragma unroll
-            for (int g = 1; g < NTM; ++g) {
-                if (g < cnt) {
-                    const int I = J + g;
-                    st_acc_sw(tiles + (I * (I - 1) / 2 + J) * 64, lo, acc[g][0], acc[g][1]);
-                }
-            }
-            if (r < 2) {
-                rhs_s[J * 16 + r * 8 + 2 * q] = accr[0];
-                rhs_s[J * 16 + r * 8 + 2 * q + 1] = accr[1];
-            }
-            __syncwarp();
             // ------------------------------------------------------------ T: L_IJ = C_IJ W^T
             const double2 wf = ld_frag_sw(wscr, lo);
-            double t[NTM][2], tr[2] = {0.0, 0.0};
 #pragma unroll
-            for (int g = 1; g < NTM; ++g) {
-                if (g < cnt) {
-                    const int I = J + g;
-                    const double2 av = ld_frag_sw(tiles + (I * (I - 1) / 2 + J) * 64, lo);
-                    t[g][0] = t[g][1] = 0.0;
-                    dmma(t[g][0], t[g][1], av.x, wf.x);
-                    dmma(t[g][0], t[g][1], av.y, wf.y);
-                }
-            }
-            {
-                const double a0 = (r < 2) ? rhs_s[J * 16 + r * 8 + q] : 0.0;
-                const double a1 = (r < 2) ? rhs_s[J * 16 + r * 8 + q + 4] : 0.0;
-                dmma(tr[0], tr[1], a0, wf.x);
-                dmma(tr[0], tr[1], a1, wf.y);
-            }
-            __syncwarp();
+            for (int g0 = 0; g0 < NTM; g0 += 4) {
+                if (g0 < cnt) {
+                    double t[4][2], tr[2] = {0.0, 0.0};
+                    double2 pv[4];
 #pragma unroll
-            for (int g = 1; g < NTM; ++g) {
-                if (g < cnt) {
-                    const int I = J + g;
-                    st_acc_sw(tiles + (I * (I - 1) / 2 + J) * 64, lo, t[g][0], t[g][1]);
+                    for (int gg = 0; gg < 4; ++gg) {
+                        const int g = g0 + gg;
+                        t[gg][0] = t[gg][1] = 0.0;
+                        if (g > 0 && g < NTM && g < cnt) {
+                            const int I = J + g;
+                            pv[gg] = ld_frag_sw(tiles + (I * (I - 1) / 2 + J) * 64, lo);
+                        }
+                    }
+                    double ra0 = 0.0, ra1 = 0.0;
+                    if (g0 == 0 && r < 2) {
+                        ra0 = rhs_s[J * 16 + r * 8 + q];
+                        ra1 = rhs_s[J * 16 + r * 8 + q + 4];
+                    }
+#pragma unroll
+                    for (int gg = 0; gg < 4; ++gg)
+                        if (g0 + gg > 0 && g0 + gg < NTM && g0 + gg < cnt) dmma(t[gg][0], t[gg][1], pv[gg].x, wf.x);
+                    if (g0 == 0) dmma(tr[0], tr[1], ra0, wf.x);
+#pragma unroll
+                    for (int gg = 0; gg < 4; ++gg)
+                        if (g0 + gg > 0 && g0 + gg < NTM && g0 + gg < cnt) dmma(t[gg][0], t[gg][1], pv[gg].y, wf.y);
+                    if (g0 == 0) dmma(tr[0], tr[1], ra1, wf.y);
+                    // every lane's operand loads are complete once the DMMAs have issued (warp-synchronous)
+#pragma unroll
+                    for (int gg = 0; gg < 4; ++gg) {
+                        const int g = g0 + gg;
+                        if (g > 0 && g < NTM && g < cnt) {
+                            const int I = J + g;
+                            st_acc_sw(tiles + (I * (I - 1) / 2 + J) * 64, lo, t[gg][0], t[gg][1]);
+                        }
+                    }
+                    if (g0 == 0 && r < 2) {
+                        rhs_s[J * 16 + r * 8 + 2 * q] = tr[0];
+                        rhs_s[J * 16 + r * 8 + 2 * q + 1] = tr[1];
+                    }
                 }
-            }
-            if (r < 2) {
-                rhs_s[J * 16 + r * 8 + 2 * q] = tr[0];
-                rhs_s[J * 16 + r * 8 + 2 * q + 1] = tr[1];
             }
             __syncwarp();
         }
@@ -307,7 +356,8 @@ static cudaError_t launch_small_t(const NllArgs& a, int mode, cudaStream_t st) {
     const size_t per_sm = 228 * 1024, reserved = 1024;
     const size_t fixed = (EXP_TAB + 8 * NTM) * 8, per_warp = (size_t)small_warp_doubles(NTM) * 8;
     int best_w = 0, best_wpc = 1;
-    for (int wpc = 1; wpc <= 8; ++wpc) {  // warps (candidates) per CTA maximising resident warps per SM
+    const int wpc_max = 8;
+    for (int wpc = 1; wpc <= wpc_max; ++wpc) {  // warps (candidates) per CTA maximising resident warps per SM
         const size_t sm = fixed + wpc * per_warp;
         if (sm > smem_optin()) break;
         int ctas = (int)(per_sm / (sm + reserved));
@@ -326,10 +376,13 @@ static cudaError_t launch_small_t(const NllArgs& a, int mode, cudaStream_t st) {
     if (mode == 0) {
         e = cudaFuncSetAttribute(krig_nll_small_kernel<NTM, KD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        // without this the driver may pick a carve-out that only fits ONE of the two CTAs per SM
+        cudaFuncSetAttribute(krig_nll_small_kernel<NTM, KD, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         krig_nll_small_kernel<NTM, KD, 0><<<(int)grid, 32 * best_wpc, smem, st>>>(a);
     } else {
         e = cudaFuncSetAttribute(krig_nll_small_kernel<NTM, KD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        cudaFuncSetAttribute(krig_nll_small_kernel<NTM, KD, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         krig_nll_small_kernel<NTM, KD, 1><<<(int)grid, 32 * best_wpc, smem, st>>>(a);
     }
     return cudaGetLastError();
