@@ -39,6 +39,7 @@ NllPlan plan_nll(int n);
 size_t nll_smem_bytes(int npad, int slots, int nwarps, size_t tile_bytes);
 cudaError_t launch_nll(NllArgs a, int mode, cudaStream_t st, long long* launches);
 cudaError_t launch_nll_small(const NllArgs& a, int mode, cudaStream_t st);
+cudaError_t launch_nll_large(NllArgs a, int mode, cudaStream_t st);
 cudaError_t launch_dtab(const double* X, int n, int k, int npad, const double* p_axis, int P, double* D, cudaStream_t st);
 cudaError_t launch_logtab(const double* X, int n, int k, int npad, double* LG, cudaStream_t st);
 cudaError_t launch_argmin(const double* v, long long C, long long c_begin, double* best_val, long long* best_idx,

@@ -186,4 +186,20 @@ __device__ __forceinline__ double nll_epilogue(const double* rhs_row, int n, int
     return 0.5 * n * log(s2) + logdet_half;
 }
 
+struct NllRhs {  // row 0 = y^T, row 1 = 1^T, rows 2..7 = 0
+    const double* y;
+    int n;
+    __device__ __forceinline__ void operator()(int rr, int j, double& v0, double& v1) const {
+        v0 = 0.0;
+        v1 = 0.0;
+        if (rr == 0) {
+            if (j < n) v0 = y[j];
+            if (j + 1 < n) v1 = y[j + 1];
+        } else if (rr == 1) {
+            if (j < n) v0 = 1.0;
+            if (j + 1 < n) v1 = 1.0;
+        }
+    }
+};
+
 }  // namespace smb
