@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIBDIR, 'libsurrogate_b200.so')
 SOURCES = ['capi.cu', 'krig_nll.cu', 'krig_nll_small.cu', 'krig_nll_large.cu', 'krig_fit.cu', 'krig_predict.cu', 'rbf.cu']
-NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
+NVCC_FLAGS = ([f'-D{d}' for d in os.environ.get('SMB_DEFINES', '').split(',') if d]) + ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC']
 
 

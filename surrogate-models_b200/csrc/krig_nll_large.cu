@@ -24,7 +24,7 @@ namespace smb {
 
 constexpr int LW = 8;   // warps per CTA
 constexpr int MB = 4;   // tile columns per macro column
-constexpr int STAGES = 4;  // operand ring depth (k-steps in flight per warp)
+constexpr int STAGES = 3;  // operand ring depth (k-steps in flight per warp); 2 CTAs x 8 warps x 3 x 4 KB = 192 KB
 
 // R entries (i, j), (i, j+1) for this lane.  The table loads of a chunk of 4 dimensions are issued together
 // and the next chunk is requested before the current one is evaluated (a runtime d-loop with one dependent
@@ -140,7 +140,7 @@ __device__ __forceinline__ bool diag_factor_plain(double c0, double c1, double* 
     return ok;
 }
 
-__global__ void __launch_bounds__(LW * 32, 1) krig_nll_large_kernel(const NllArgs a, const int mode) {
+__global__ void __launch_bounds__(LW * 32, 2) krig_nll_large_kernel(const NllArgs a, const int mode) {
     __shared__ double etab[EXP_TAB];
     __shared__ double th_s[KMAX], pw_s[KMAX];
     __shared__ long long off_s[KMAX];
@@ -365,10 +365,11 @@ __global__ void __launch_bounds__(LW * 32, 1) krig_nll_large_kernel(const NllArg
     }
 }
 
-// n > 64 (or k > 4): macro-panel kernel on a global workspace.  Returns cudaErrorNotSupported for n <= 64.
+// n > 128: macro-panel kernel on a global workspace.  Returns cudaErrorNotSupported for smaller n.
 cudaError_t launch_nll_large(NllArgs a, int mode, cudaStream_t st) {
     const int NT = a.npad / 8;
-    if (NT <= 8 && a.k <= 4) return cudaErrorNotSupported;
+    // n <= 128 stays on the shared-memory tile engine (measured: 2.65 vs 2.25 TFLOP/s at n = 128)
+    if (NT <= 16) return cudaErrorNotSupported;
     if (a.C <= 0) return cudaSuccess;
     const size_t tile_bytes = chol_tiles(NT, 1) * 512;
     const size_t smem = (size_t)a.npad * 8 + (size_t)LW * STAGES * 8 * 512;
