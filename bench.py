@@ -136,7 +136,7 @@ class ClockSampler:
         try:
             self.fh = open(self.path, 'w')
             self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits',
-                                          '-lms', '100', '-i', str(self.index)], stdout=self.fh,
+                                          '-lms', '50', '-i', str(self.index)], stdout=self.fh,
                                          stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -295,24 +295,62 @@ def run_gpu(args):
            'api': 'sm_krig_nll_grid_host (pinned host buffers)'}
     assert int(bih.item()) == best_idx
 
-    # ---- secondary: predictions/s (value + MSE) on the kriging_r3 model, queries resident in HBM
+    # ---- secondary figures (device-timed, inputs resident in HBM): the other BASELINE configs at bounded size
+    def timed_ms(fn, reps=2):
+        fn()
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b))
+        return best
+
+    # C5: predictions/s (value + MSE) on the kriging_r3 model
     X5, y5 = workloads.c5_kriging_r3()
     k5 = Kriging(X5, y5)
     k5.update_param([0.05, 0.05], [1.9, 1.9])
     m = 3162  # 3162^2 ~ 1e7 mesh points per GPU over [-2, 12]^2
     xq = device.to_dev(workloads.c5_query_mesh(m))
-    for _ in range(2):
-        k5.predict_device(xq, True)
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    k5.predict_device(xq, True)
-    b.record()
-    torch.cuda.synchronize()
-    pred_ms = a.elapsed_time(b)
+    pred_ms = timed_ms(lambda: k5.predict_device(xq, True))
+    pred_mean_ms = timed_ms(lambda: k5.predict_device(xq, False))
     secondary = {'metric': 'kriging predictions/s (value+MSE, n=36, k=2, p=1.9)', 'value': world * m * m / (pred_ms * 1e-3),
                  'unit': 'predictions/s', 'queries_per_gpu': m * m, 'ms': pred_ms,
-                 'hbm_gbs_achieved': m * m * 32 / (pred_ms * 1e-3) / 1e9}
+                 'hbm_gbs_achieved': m * m * 32 / (pred_ms * 1e-3) / 1e9,
+                 'mean_only_predictions_per_s': world * m * m / (pred_mean_ms * 1e-3)}
+    del xq
+    # C3: 8-D Kriging, n = 1024 LHS samples, explicit candidate list (592 candidates per GPU here)
+    X3, y3 = workloads.c3_lhs1024()
+    e3, p3 = workloads.c3_candidates(592 * world, 8)
+    k3 = Kriging(X3, y3)
+    d3 = k3._dev()
+    th3 = device.to_dev(np.power(10., e3[rank * 592:(rank + 1) * 592]))
+    pp3 = device.to_dev(p3[rank * 592:(rank + 1) * 592])
+    out3 = device.empty(592)
+    c3_ms = timed_ms(lambda: _cabi.check(L.sm_krig_nll_batch(device.ptr(d3['X']), device.ptr(d3['y']), 1024, 8, device.ptr(th3),
+                                                               device.ptr(pp3), 592, 0, device.ptr(out3), None, None, stream)))
+    secondary_c3 = {'metric': 'kriging likelihood evaluations/s (n=1024, k=8, list mode)', 'value': world * 592 / (c3_ms * 1e-3),
+                    'unit': 'evals/s', 'candidates_per_gpu': 592, 'ms': c3_ms,
+                    'tflops_fma_only': flops_like(1024, 8) * 592 / (c3_ms * 1e-3) / 1e12,
+                    'frac_of_fp64_peak': flops_like(1024, 8) * 592 / (c3_ms * 1e-3) / 1e12 / peak_tf}
+    # C4: gaussian RBF, n = 4096: weight solve + evaluation at 2e6 points per GPU
+    from mylibs.rbf import RBF
+    X4, y4 = workloads.c4_rbf4096()
+    r4 = RBF(X4, y4)
+    t0 = time.perf_counter()
+    r4.update_param(1.0, 'gaus')
+    torch.cuda.synchronize()
+    fit_s = time.perf_counter() - t0
+    nq4 = 2000000
+    xq4 = device.to_dev(workloads.c4_queries(nq4, seed=1 + rank))
+    c4_ms = timed_ms(lambda: r4.predict_device(xq4))
+    secondary_c4 = {'metric': 'rbf evaluations/s (gaus, n=4096, k=3)', 'value': world * nq4 / (c4_ms * 1e-3), 'unit': 'predictions/s',
+                    'queries_per_gpu': nq4, 'ms': c4_ms, 'weight_solve_s': fit_s,
+                    'kernel_evals_per_s': world * nq4 * 4096 / (c4_ms * 1e-3)}
+    del xq4
 
     if rank == 0:
         cpu = None
@@ -335,7 +373,7 @@ def run_gpu(args):
                        'candidates_per_gpu': CAND_PER_GPU, 'l2': 'flushed (256 MiB write) between timed steps',
                        'parallelism': f'candidate-sharded x{world}; all_gather of (nll_min, index) only'},
             'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline,
-            'cpu_baseline': cpu, 'secondary': secondary,
+            'cpu_baseline': cpu, 'secondary': secondary, 'secondary_c3': secondary_c3, 'secondary_c4': secondary_c4,
             'result': {'best_idx': best_idx, 'best_nll': best_val},
         }
         print(json.dumps(line), flush=True)
