@@ -18,6 +18,7 @@ struct NllArgs {
     const double* theta_axis;
     int T, P;
     const double* dtab;  // [k][P][npad][npad]
+    const double* egrid;  // optional [k][P][T][npad][npad]: exp(-theta_axis[t] * dtab) -- product-form entries
     // list mode (MODE 1)
     const double* theta;  // [C][k] linear
     const double* p;      // [C][k]
@@ -41,6 +42,7 @@ cudaError_t launch_nll(NllArgs a, int mode, cudaStream_t st, long long* launches
 cudaError_t launch_nll_small(const NllArgs& a, int mode, cudaStream_t st);
 cudaError_t launch_nll_large(NllArgs a, int mode, cudaStream_t st);
 cudaError_t launch_dtab(const double* X, int n, int k, int npad, const double* p_axis, int P, double* D, cudaStream_t st);
+cudaError_t launch_egrid(const double* dtab, const double* theta_axis, int k, int P, int T, int npad, double* E, cudaStream_t st);
 cudaError_t launch_logtab(const double* X, int n, int k, int npad, double* LG, cudaStream_t st);
 cudaError_t launch_argmin(const double* v, long long C, long long c_begin, double* best_val, long long* best_idx,
                           cudaStream_t st);

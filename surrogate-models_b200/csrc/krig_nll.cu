@@ -42,6 +42,18 @@ __global__ void dtab_kernel(const double* __restrict__ X, int n, int k, int npad
     }
 }
 
+// E[d][q][t][i][j] = exp(-theta_axis[t] * D[d][q][i][j]): in grid mode the candidates only combine T theta
+// values per dimension, so R_ij = prod_d E[d][q_d][t_d][i][j] needs one multiply per entry instead of an exp
+// (the exp evaluations are ~25 % of the fp64-pipe time of the n = 64 kernel).  Padding: D = DBL_MAX -> 0.
+__global__ void egrid_kernel(const double* __restrict__ D, const double* __restrict__ theta_axis, int T, size_t per,
+                             size_t ntab, double* __restrict__ E) {
+    const size_t total = ntab * T * per;
+    for (size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x; x < total; x += (size_t)gridDim.x * blockDim.x) {
+        const size_t ij = x % per, tt = (x / per) % T, dq = x / (per * T);
+        E[x] = exp(-__dmul_rn(theta_axis[tt], D[dq * per + ij]));
+    }
+}
+
 __global__ void logtab_kernel(const double* __restrict__ X, int n, int k, int npad, double* __restrict__ LG) {
     const size_t per = (size_t)npad * npad;
     const size_t total = per * k;
@@ -350,6 +362,13 @@ cudaError_t launch_dtab(const double* X, int n, int k, int npad, const double* p
     int grid = (int)((total + 255) / 256);
     if (grid > 148 * 16) grid = 148 * 16;
     dtab_kernel<<<grid, 256, 0, st>>>(X, n, k, npad, p_axis, P, D);
+    return cudaGetLastError();
+}
+cudaError_t launch_egrid(const double* dtab, const double* theta_axis, int k, int P, int T, int npad, double* E, cudaStream_t st) {
+    const size_t per = (size_t)npad * npad, ntab = (size_t)k * P;
+    size_t blocks = (ntab * T * per + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    egrid_kernel<<<(int)blocks, 256, 0, st>>>(dtab, theta_axis, T, per, ntab, E);
     return cudaGetLastError();
 }
 cudaError_t launch_logtab(const double* X, int n, int k, int npad, double* LG, cudaStream_t st) {

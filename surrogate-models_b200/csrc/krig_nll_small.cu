@@ -59,6 +59,16 @@ __device__ __forceinline__ void load_pair(const SmallParams<KD>& P, int off0, in
 template <int KD, int MODE>
 __device__ __forceinline__ void eval_entry(const SmallParams<KD>& P, const double2 (&t)[KD], const double* etab,
                                            double& v0, double& v1) {
+    if (MODE == 2) {  // product form: the table already holds exp(-theta_d D_d)
+        v0 = t[0].x;
+        v1 = t[0].y;
+#pragma unroll
+        for (int d = 1; d < KD; ++d) {
+            v0 *= t[d].x;
+            v1 *= t[d].y;
+        }
+        return;
+    }
     double s0 = 0.0, s1 = 0.0;
 #pragma unroll
     for (int d = 0; d < KD; ++d) {
@@ -157,7 +167,7 @@ __global__ void __launch_bounds__(256, 2) krig_nll_small_kernel(const NllArgs a)
     for (long long c = first; c < a.C; c += stride) {
         // ---------------------------------------------------------------- candidate parameters
         SmallParams<KD> P;
-        if (MODE == 0) {
+        if (MODE == 0 || MODE == 2) {
             long long tk = 1;
 #pragma unroll
             for (int d = 0; d < KD; ++d) tk *= a.T;
@@ -165,8 +175,13 @@ __global__ void __launch_bounds__(256, 2) krig_nll_small_kernel(const NllArgs a)
             long long it = cg % tk, ip = cg / tk;
 #pragma unroll
             for (int d = 0; d < KD; ++d) {
-                P.th[d] = a.theta_axis[it % a.T];
-                P.tab[d] = a.dtab + ((long long)d * a.P + (ip % a.P)) * per;
+                if (MODE == 0) {
+                    P.th[d] = a.theta_axis[it % a.T];
+                    P.tab[d] = a.dtab + ((long long)d * a.P + (ip % a.P)) * per;
+                } else {
+                    P.th[d] = 0.0;
+                    P.tab[d] = a.egrid + (((long long)d * a.P + (ip % a.P)) * a.T + (it % a.T)) * per;
+                }
                 it /= a.T;
                 ip /= a.P;
             }
@@ -373,7 +388,12 @@ static cudaError_t launch_small_t(const NllArgs& a, int mode, cudaStream_t st) {
     const long long need = (a.C + best_wpc - 1) / best_wpc;
     if (grid > need) grid = need;
     cudaError_t e;
-    if (mode == 0) {
+    if (mode == 0 && a.egrid) {
+        e = cudaFuncSetAttribute(krig_nll_small_kernel<NTM, KD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        cudaFuncSetAttribute(krig_nll_small_kernel<NTM, KD, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        krig_nll_small_kernel<NTM, KD, 2><<<(int)grid, 32 * best_wpc, smem, st>>>(a);
+    } else if (mode == 0) {
         e = cudaFuncSetAttribute(krig_nll_small_kernel<NTM, KD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         // without this the driver may pick a carve-out that only fits ONE of the two CTAs per SM
