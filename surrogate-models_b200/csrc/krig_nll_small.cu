@@ -122,9 +122,9 @@ __device__ __forceinline__ bool diag_factor(double c0, double c1, double* __rest
         const double d = ts[j * 8 + j];
         const double vr = ts[j * 8 + r];
         const double2 vc = *reinterpret_cast<const double2*>(ts + j * 8 + 2 * q);
-        ok = ok && (d > 0.0);
+        ok = ok && (d > 1e-36);  // below that R is numerically singular (and the fp32 seed would underflow)
         tp *= d;
-        const double inv = rsqrt(d);
+        const double inv = rsqrt_pivot(d);
         const double t = vr * (inv * inv);
         c0 = fma(-t, vc.x, c0);
         c1 = fma(-t, vc.y, c1);

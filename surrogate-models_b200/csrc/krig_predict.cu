@@ -9,25 +9,26 @@
 // psi for (sample 8K + l%4 + 4h, query l/4), which is exactly the element mma.m8n8k4 wants from it.
 // With c in hand the mean comes for free as mu + rres . c  (rres = L^-1 (y - 1 mu)).
 #include "common.cuh"
+#include "fastmath.cuh"
 #include "kernels.h"
 
 namespace smb {
 
-__device__ __forceinline__ double pow_abs(double dx, double p) {
+__device__ __forceinline__ double pow_abs(double dx, double p, const PowTables& T) {
     // abs(dx) ** p of the reference; p == 2 and p == 1 are exact in libm pow, so the shortcuts are too
     if (p == 2.0) return dx * dx;
     if (p == 1.0) return dx;
-    return pow(dx, p);
+    return dx == 0.0 ? 0.0 : pow_pos(dx, p, T);  // table-driven, <= 1 ulp (fastmath.cuh)
 }
 
 template <int KD>
 __device__ __forceinline__ double psi_one(const double* __restrict__ xs, const double* xq, const double* th,
-                                          const double* pw, int k) {
+                                          const double* pw, int k, const PowTables& T) {
     double s = 0.0;
     const int kk = KD > 0 ? KD : k;
 #pragma unroll
-    for (int d = 0; d < kk; ++d) s = __dadd_rn(s, __dmul_rn(th[d], pow_abs(fabs(xs[d] - xq[d]), pw[d])));
-    return exp(-s);
+    for (int d = 0; d < kk; ++d) s = __dadd_rn(s, __dmul_rn(th[d], pow_abs(fabs(xs[d] - xq[d]), pw[d], T)));
+    return exp_fast<false>(-s, T.e);
 }
 
 // ------------------------------------------------------------------------------------ mean only
@@ -38,6 +39,8 @@ __global__ void __launch_bounds__(256) krig_predict_mean_kernel(const PredictArg
     double* w_s = X_s + (size_t)a.n * a.k;   // [n]
     double* th_s = w_s + a.n;                // [KMAX]
     double* p_s = th_s + KMAX;               // [KMAX]
+    __shared__ PowTables PT;
+    PT.init(threadIdx.x, blockDim.x);
     for (int t = threadIdx.x; t < a.n * a.k; t += blockDim.x) X_s[t] = a.X[t];
     for (int t = threadIdx.x; t < a.n; t += blockDim.x) w_s[t] = a.w[t];
     if (threadIdx.x < a.k) {
@@ -52,7 +55,7 @@ __global__ void __launch_bounds__(256) krig_predict_mean_kernel(const PredictArg
 #pragma unroll
         for (int d = 0; d < kk; ++d) xq[d] = a.Xq[q * k + d];
         double acc = 0.0;
-        for (int i = 0; i < a.n; ++i) acc = fma(psi_one<KD>(X_s + (size_t)i * k, xq, th_s, p_s, k), w_s[i], acc);
+        for (int i = 0; i < a.n; ++i) acc = fma(psi_one<KD>(X_s + (size_t)i * k, xq, th_s, p_s, k, PT), w_s[i], acc);
         a.y_out[q] = a.mu + acc;
     }
 }
@@ -71,6 +74,8 @@ __global__ void __launch_bounds__(256) krig_predict_mse_kernel(const PredictArgs
     double* th_s = r_s + a.npad;                     // [KMAX]
     double* p_s = th_s + KMAX;                       // [KMAX]
     double* bb_s = p_s + KMAX;                       // [1]
+    __shared__ PowTables PT;
+    PT.init(threadIdx.x, blockDim.x);
     for (size_t t = threadIdx.x; t < ntile * 64; t += blockDim.x) M_s[t] = a.Mop[t];
     for (int t = threadIdx.x; t < a.npad * k; t += blockDim.x) X_s[t] = (t < a.n * k) ? a.X[t] : 0.0;
     for (int t = threadIdx.x; t < a.npad; t += blockDim.x) {
@@ -125,8 +130,8 @@ __global__ void __launch_bounds__(256) krig_predict_mse_kernel(const PredictArgs
 #pragma unroll
                 for (int g = 0; g < QG; ++g) {
                     double v;
-                    if (KD > 0) v = psi_one<KD>(X_s + (size_t)i * k, xq[g], th_s, p_s, k);
-                    else v = psi_one<0>(X_s + (size_t)i * k, a.Xq + qidx[g] * k, th_s, p_s, k);
+                    if (KD > 0) v = psi_one<KD>(X_s + (size_t)i * k, xq[g], th_s, p_s, k, PT);
+                    else v = psi_one<0>(X_s + (size_t)i * k, a.Xq + qidx[g] * k, th_s, p_s, k, PT);
                     psi[g][h] = (i < a.n) ? v : 0.0;
                 }
             }
@@ -180,6 +185,8 @@ __global__ void __launch_bounds__(256) krig_predict_mse_kernel(const PredictArgs
 // thread per query, psi staged in a global scratch [n][Q] (coalesced), M read tile-wise (L1 broadcast)
 __global__ void __launch_bounds__(256) krig_predict_mse_generic_kernel(const PredictArgs a, double* __restrict__ psi_ws) {
     __shared__ double th_s[KMAX], p_s[KMAX], red[8];
+    __shared__ PowTables PT;
+    PT.init(threadIdx.x, blockDim.x);
     const int k = a.k, n = a.n;
     if (threadIdx.x < k) {
         th_s[threadIdx.x] = a.theta[threadIdx.x];
@@ -197,7 +204,7 @@ __global__ void __launch_bounds__(256) krig_predict_mse_generic_kernel(const Pre
     double* my = psi_ws + t;
     for (long long q = t; q < a.Nq; q += Q) {
         const double* xq = a.Xq + q * k;
-        for (int i = 0; i < n; ++i) my[(size_t)i * Q] = psi_one<0>(a.X + (size_t)i * k, xq, th_s, p_s, k);
+        for (int i = 0; i < n; ++i) my[(size_t)i * Q] = psi_one<0>(a.X + (size_t)i * k, xq, th_s, p_s, k, PT);
         double cc = 0.0, bc = 0.0, rc = 0.0;
         for (int row = 0; row < n; ++row) {
             const int Rt = row >> 3, r = row & 7;
