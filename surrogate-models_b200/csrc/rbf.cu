@@ -7,6 +7,7 @@
 // The gaussian kernel matrix is SPD: it goes through the same DMMA tile Cholesky as the Kriging
 // likelihood, followed by a tile back-substitution.  The other kernels are not definite and use LU with
 // partial pivoting (what np.linalg.solve does), as does a gaussian matrix that is not numerically SPD.
+#include "fastmath.cuh"
 #include "tile_chol.cuh"
 #include "kernels.h"
 
@@ -245,6 +246,8 @@ __global__ void __launch_bounds__(256) rbf_predict_kernel(const double* __restri
     extern __shared__ __align__(16) double smem[];
     double* X_s = smem;                          // [chunk][k]
     double* c_s = X_s + (size_t)RBF_CHUNK * k;   // [chunk]
+    __shared__ double etab[EXP_TAB];
+    exp_table_init(etab, threadIdx.x, blockDim.x);
     const int kk = KD > 0 ? KD : k;
     const long long Q = (long long)gridDim.x * blockDim.x;
     const long long nrounds = (Nq + Q - 1) / Q;
@@ -268,7 +271,14 @@ __global__ void __launch_bounds__(256) rbf_predict_kernel(const double* __restri
                     const double dx = xq[d] - X_s[(size_t)i * k + d];
                     s = __dadd_rn(s, __dmul_rn(dx, dx));
                 }
-                res = fma(c_s[i], rbf_phi(kind, a, sqrt(s)), res);  // res += coeff_i * phi
+                double phi;
+                if (kind == 2) {  // gaussian: e^-(a r)^2 = e^-(a^2 s): no sqrt (the argument differs from the
+                    // reference's sqrt-then-square by <= 2 ulp, i.e. <= 1e-16 absolute on phi); table-driven exp
+                    phi = exp_fast<false>(-((a * a) * s), etab);
+                } else {
+                    phi = rbf_phi(kind, a, sqrt(s));
+                }
+                res = fma(c_s[i], phi, res);  // res += coeff_i * phi
             }
         }
         if (live) y_out[q] = res;
