@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(256) krig_fit_kernel(const double* __restrict_
     __syncthreads();
     const DirectEntry e{X, th_s, p_s, k, n};
     const FitRhs rhs{y, n};
-    const CholResult res = tile_cholesky<8, 4, true>(tiles, NT, NT + 1, e, rhs, wscr + wid * 64, wid, lane);
+    const CholResult res = tile_cholesky<8, 4, 1>(tiles, NT, NT + 1, e, rhs, wscr + wid * 64, wid, lane);
     const double* rhs_base = tiles + (size_t)NT * (NT + 1) / 2 * 64;
     if (!res.ok) {
         if (threadIdx.x == 0) {

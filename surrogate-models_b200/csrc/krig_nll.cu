@@ -177,10 +177,10 @@ krig_nll_kernel(const NllArgs a) {
         CholResult res;
         if (MODE == 0) {
             const GridEntry e{th, reinterpret_cast<const long long*>(pw), a.dtab, a.k, a.n, a.npad};
-            res = tile_cholesky<WARPS, 4, false>(tiles, NT, 1, e, rhs, wscratch, ewid, lane);
+            res = tile_cholesky<WARPS, 4, -1>(tiles, NT, 1, e, rhs, wscratch, ewid, lane);
         } else {
             const ListEntry e{th, pw, a.logtab, a.k, a.n, a.npad};
-            res = tile_cholesky<WARPS, 4, false>(tiles, NT, 1, e, rhs, wscratch, ewid, lane);
+            res = tile_cholesky<WARPS, 4, -1>(tiles, NT, 1, e, rhs, wscratch, ewid, lane);
         }
         if (ewid == 0) {
             double nll = INFINITY;

@@ -5,8 +5,10 @@
 // kernels (rbf.py:105-118): 0 lin r | 1 cubic r^3 | 2 gaus e^-(a r)^2 | 3 mq sqrt(1+(a r)^2)
 //                           4 imq (1 + r^2)^(a/2)   (the reference's own formula, kept as is)
 // The gaussian kernel matrix is SPD: it goes through the same DMMA tile Cholesky as the Kriging
-// likelihood, followed by a tile back-substitution.  The other kernels are not definite and use LU with
+// likelihood -- as ONE matrix spread over a cooperative grid -- followed by a tile back-substitution.  The other kernels are not definite and use LU with
 // partial pivoting (what np.linalg.solve does), as does a gaussian matrix that is not numerically SPD.
+#include <cooperative_groups.h>
+
 #include "fastmath.cuh"
 #include "tile_chol.cuh"
 #include "kernels.h"
@@ -54,43 +56,162 @@ struct RbfRhs {  // row 0 = y^T
     }
 };
 
-// SPD solve: Phi = L L^T (tile engine), a = L^-1 y, then L^T c = a by tile back-substitution.
-__global__ void __launch_bounds__(256) rbf_fit_chol_kernel(const double* __restrict__ X, const double* __restrict__ y,
-                                                           int n, int k, int kind, double a,
-                                                           double* __restrict__ tiles, double* __restrict__ coeff,
-                                                           double* __restrict__ xwork, int* __restrict__ info) {
-    __shared__ double wscr[8 * 64];
+// ------------------------------------------------------------------------------------ cooperative SPD solve
+// One matrix, the whole GPU: Phi = L L^T with the macro-column scheme of krig_nll_large.cu spread over every
+// warp of a cooperative grid (a single CTA took 0.54 s at n = 4096).  Per macro column (4 tile columns):
+//   A   every warp takes (row tile, column pair) items: C = Phi - sum_{K<J0} L_IK L_JK^T   (entries fused)
+//   P1  warp 0 of CTA 0 factors the <= 32 x 32 diagonal block with identity right-hand sides (tile engine in
+//       shared memory): the block's L tiles, the inverse diagonal tiles W and S = L_blk^-T
+//   P3  every warp solves row tiles of the panel: L[I, J0+b] = sum_{a<=b} C[I, J0+a] S(a, b)
+// with a grid-wide barrier between the phases (3 per macro column).  y rides along as tile row NT.
+// Finally CTA 0 back-substitutes L^T c = L^-1 y.
+namespace cg = cooperative_groups;
+constexpr int CMB = 4;
+
+__global__ void __launch_bounds__(256, 1) rbf_fit_coop_kernel(const double* __restrict__ X, const double* __restrict__ y,
+                                                             int n, int k, int kind, double a_par,
+                                                             double* __restrict__ tiles, double* __restrict__ sblk,
+                                                             double* __restrict__ coeff, double* __restrict__ xwork,
+                                                             int* __restrict__ flag, int* __restrict__ info) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ __align__(16) double blk_s[(CMB * (CMB + 1) / 2 + CMB * CMB) * 64];
     __shared__ double cj[8];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int NT = (n + 7) / 8, npad = NT * 8;
-    const RbfEntry e{X, k, n, kind, a};
+    const int r = lane >> 2, q = lane & 3;
+    const int NT = (n + 7) / 8, NI = NT + 1, npad = NT * 8;
+    const int gw = blockIdx.x * 8 + wid, GW = gridDim.x * 8;
+    const RbfEntry entry{X, k, n, kind, a_par};
     const RbfRhs rhs{y, n};
-    const CholResult res = tile_cholesky<8, 4, false>(tiles, NT, 1, e, rhs, wscr + wid * 64, wid, lane);
-    if (!res.ok) {
+    double* const rhs_base = tiles + (size_t)NT * (NT + 1) / 2 * 64;
+    auto tile_ptr = [&](int I, int K) -> double* {
+        return (I < NT) ? tiles + ((size_t)I * (I + 1) / 2 + K) * 64 : rhs_base + (size_t)K * 64;
+    };
+    bool ok = true;
+    for (int J0 = 0; J0 < NT; J0 += CMB) {
+        const int ncol = min(CMB, NT - J0);
+        // ---------------------------------------------------------------- A: entries + bulk update, 1 x 2 tiles per item
+        const int nitem = (NI - J0) * 2;
+        for (int it = gw; it < nitem; it += GW) {
+            const int I = J0 + (it >> 1), jb = (it & 1) * 2;  // columns J0 + jb, J0 + jb + 1
+            if (jb >= ncol) continue;
+            double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+            const double* ap = tile_ptr(I, 0) + 2 * lane;
+            const double* bp0 = tile_ptr(min(J0 + jb, NT - 1), 0) + 2 * lane;
+            const double* bp1 = tile_ptr(min(J0 + jb + 1, NT - 1), 0) + 2 * lane;
+            if (J0 > 0) {
+                double2 ca = __ldcg(reinterpret_cast<const double2*>(ap));
+                double2 cb0 = __ldcg(reinterpret_cast<const double2*>(bp0));
+                double2 cb1 = __ldcg(reinterpret_cast<const double2*>(bp1));
+                for (int K = 0; K < J0; ++K) {
+                    const int Kn = (K + 1 < J0) ? K + 1 : K;
+                    const double2 na = __ldcg(reinterpret_cast<const double2*>(ap + (size_t)Kn * 64));
+                    const double2 nb0 = __ldcg(reinterpret_cast<const double2*>(bp0 + (size_t)Kn * 64));
+                    const double2 nb1 = __ldcg(reinterpret_cast<const double2*>(bp1 + (size_t)Kn * 64));
+                    dmma(acc[0][0], acc[0][1], ca.x, cb0.x);
+                    dmma(acc[1][0], acc[1][1], ca.x, cb1.x);
+                    dmma(acc[0][0], acc[0][1], ca.y, cb0.y);
+                    dmma(acc[1][0], acc[1][1], ca.y, cb1.y);
+                    ca = na;
+                    cb0 = nb0;
+                    cb1 = nb1;
+                }
+            }
+#pragma unroll
+            for (int jj = 0; jj < 2; ++jj) {
+                const int J = J0 + jb + jj;
+                if (jb + jj < ncol && (I >= NT || J <= I)) {
+                    double v0, v1;
+                    if (I < NT) entry(8 * I + r, 8 * J + 2 * q, v0, v1);
+                    else rhs(r, 8 * J + 2 * q, v0, v1);
+                    st_acc(tile_ptr(I, J), lane, v0 - acc[jj][0], v1 - acc[jj][1]);
+                }
+            }
+        }
+        grid.sync();
+        // ---------------------------------------------------------------- P1: diagonal block (one warp)
+        if (blockIdx.x == 0 && wid == 0) {
+            const BlockEntry be{tiles, J0};
+            const IdentityRhs ir{};
+            const CholResult res = tile_cholesky<1, 4, 0>(blk_s, ncol, ncol, be, ir, nullptr, 0, lane);
+            if (lane == 0 && !res.ok) *flag = 1;
+            if (res.ok) {
+                for (int aa = 0; aa < ncol; ++aa)  // L tiles of the block and the inverse diagonal tiles W
+                    for (int bb = 0; bb <= aa; ++bb)
+                        *reinterpret_cast<double2*>(tile_ptr(J0 + aa, J0 + bb) + 2 * lane) =
+                            ld_frag(blk_s + (aa * (aa + 1) / 2 + bb) * 64, lane);
+                const double* S = blk_s + (size_t)ncol * (ncol + 1) / 2 * 64;
+                for (int aa = 0; aa < ncol; ++aa)  // S(a, b) = (L_blk^-T) tile (a, b), b >= a
+                    for (int bb = aa; bb < ncol; ++bb)
+                        *reinterpret_cast<double2*>(sblk + (aa * CMB + bb) * 64 + 2 * lane) = ld_frag(S + (aa * ncol + bb) * 64, lane);
+            }
+        }
+        grid.sync();
+        if (__ldcg(flag) != 0) {
+            ok = false;
+            break;
+        }
+        // ---------------------------------------------------------------- P3: panel solve, one row tile per item
+        {
+            double2 sf[CMB][CMB];
+#pragma unroll
+            for (int aa = 0; aa < CMB; ++aa)
+#pragma unroll
+                for (int bb = aa; bb < CMB; ++bb)
+                    if (bb < ncol) {
+                        const double* st = sblk + (aa * CMB + bb) * 64;
+                        sf[aa][bb].x = __ldcg(st + tile_pos(lane & 3, lane >> 2));
+                        sf[aa][bb].y = __ldcg(st + tile_pos((lane & 3) + 4, lane >> 2));
+                    }
+            for (int I = J0 + ncol + gw; I < NI; I += GW) {
+                double2 cf[CMB];
+                double o[CMB][2];
+#pragma unroll
+                for (int aa = 0; aa < CMB; ++aa) {
+                    o[aa][0] = o[aa][1] = 0.0;
+                    if (aa < ncol) cf[aa] = __ldcg(reinterpret_cast<const double2*>(tile_ptr(I, J0 + aa) + 2 * lane));
+                }
+#pragma unroll
+                for (int aa = 0; aa < CMB; ++aa)
+#pragma unroll
+                    for (int bb = aa; bb < CMB; ++bb)
+                        if (bb < ncol) dmma(o[bb][0], o[bb][1], cf[aa].x, sf[aa][bb].x);
+#pragma unroll
+                for (int aa = 0; aa < CMB; ++aa)
+#pragma unroll
+                    for (int bb = aa; bb < CMB; ++bb)
+                        if (bb < ncol) dmma(o[bb][0], o[bb][1], cf[aa].y, sf[aa][bb].y);
+#pragma unroll
+                for (int bb = 0; bb < CMB; ++bb)
+                    if (bb < ncol) st_acc(tile_ptr(I, J0 + bb), lane, o[bb][0], o[bb][1]);
+            }
+        }
+        grid.sync();
+    }
+    if (blockIdx.x != 0) return;
+    if (!ok) {
         if (threadIdx.x == 0) *info = -1;  // not numerically SPD: caller falls back to LU
         return;
     }
-    const double* rhs_row = tiles + (size_t)NT * (NT + 1) / 2 * 64;
+    // ---------------------------------------------------------------- back-substitution L^T c = a on CTA 0
     for (int j = threadIdx.x; j < npad; j += blockDim.x)
-        xwork[j] = (j < n) ? rhs_row[(size_t)(j >> 3) * 64 + tile_pos(0, j & 7)] : 0.0;
+        xwork[j] = (j < n) ? __ldcg(rhs_base + (size_t)(j >> 3) * 64 + tile_pos(0, j & 7)) : 0.0;
     __syncthreads();
     for (int J = NT - 1; J >= 0; --J) {
         const double* rowJ = tiles + (size_t)J * (J + 1) / 2 * 64;
         if (threadIdx.x < 8) {  // c_J = W_J^T s_J
             const double* W = rowJ + (size_t)J * 64;
             double s = 0.0;
-            for (int r = 0; r < 8; ++r) s = fma(W[tile_pos(r, threadIdx.x)], xwork[8 * J + r], s);
+            for (int rr = 0; rr < 8; ++rr) s = fma(__ldcg(W + tile_pos(rr, threadIdx.x)), xwork[8 * J + rr], s);
             cj[threadIdx.x] = s;
         }
         __syncthreads();
         if (threadIdx.x < 8) xwork[8 * J + threadIdx.x] = cj[threadIdx.x];
-        // s_{I'} -= L_{J,I'}^T c_J for every I' < J
         for (int t = threadIdx.x; t < 8 * J; t += blockDim.x) {
             const double* T = rowJ + (size_t)(t >> 3) * 64;
             const int c = t & 7;
             double s = xwork[t];
 #pragma unroll
-            for (int r = 0; r < 8; ++r) s = fma(-T[tile_pos(r, c)], cj[r], s);
+            for (int rr = 0; rr < 8; ++rr) s = fma(-__ldcg(T + tile_pos(rr, c)), cj[rr], s);
             xwork[t] = s;
         }
         __syncthreads();
@@ -191,14 +312,29 @@ cudaError_t launch_rbf_fit(const double* X, const double* y, int n, int k, int k
     const int NT = (n + 7) / 8;
     int h_info = -1;
     if (kind == 2) {
-        double *tiles = nullptr, *xwork = nullptr;
+        double *tiles = nullptr, *xwork = nullptr, *sblk = nullptr;
+        int* flag = nullptr;
         e = cudaMallocAsync((void**)&tiles, chol_tiles(NT, 1) * 512, st);
         if (e != cudaSuccess) return e;
         e = cudaMallocAsync((void**)&xwork, (size_t)NT * 8 * 8, st);
         if (e != cudaSuccess) return e;
-        rbf_fit_chol_kernel<<<1, 256, 0, st>>>(X, y, n, k, kind, a, tiles, coeff, xwork, info);
+        e = cudaMallocAsync((void**)&sblk, (size_t)CMB * CMB * 512, st);
+        if (e != cudaSuccess) return e;
+        e = cudaMallocAsync((void**)&flag, sizeof(int), st);
+        if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(flag, 0, sizeof(int), st);
+        if (e != cudaSuccess) return e;
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rbf_fit_coop_kernel, 256, 0);
+        if (e != cudaSuccess) return e;
+        int grid = sm_count() * (per_sm > 0 ? 1 : 0);
+        const int useful = ((NT + 1) * 2 + 7) / 8;  // CTAs that can get a work item in the first macro column
+        if (grid > useful) grid = useful;
+        if (grid < 1) grid = 1;
+        void* args[] = {(void*)&X, (void*)&y, (void*)&n, (void*)&k, (void*)&kind, (void*)&a, (void*)&tiles, (void*)&sblk,
+                        (void*)&coeff, (void*)&xwork, (void*)&flag, (void*)&info};
+        e = cudaLaunchCooperativeKernel((const void*)rbf_fit_coop_kernel, dim3(grid), dim3(256), args, 0, st);
         if (launches) *launches += 1;
-        e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         e = cudaMemcpyAsync(&h_info, info, sizeof(int), cudaMemcpyDeviceToHost, st);
         if (e != cudaSuccess) return e;
@@ -206,6 +342,8 @@ cudaError_t launch_rbf_fit(const double* X, const double* y, int n, int k, int k
         if (e != cudaSuccess) return e;
         cudaFreeAsync(tiles, st);
         cudaFreeAsync(xwork, st);
+        cudaFreeAsync(sblk, st);
+        cudaFreeAsync(flag, st);
         if (h_info == 0) return cudaSuccess;
     }
     // LU with partial pivoting on the dense column-major matrix

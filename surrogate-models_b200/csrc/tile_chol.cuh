@@ -41,9 +41,9 @@ struct CholResult {
 // Entry(i, j, v0, v1): matrix entries (i, j), (i, j+1), j even, i/j < 8 NT (padding: identity).
 // Rhs(rr, j, v0, v1):  right-hand side row rr (< 8 NR), columns j, j+1.
 // wscratch: per-warp 64-double scratch in shared memory (layout change accumulator -> operand).
-// TRI: rhs tile rows 1.. hold identity rows (row block b is e_{8(b-1)}..): their tiles left of column
-// tile b-1 are structurally zero and are neither computed nor stored.
-template <int WARPS, int GI, bool TRI, class Entry, class Rhs>
+// TRI0 >= 0: rhs tile rows TRI0, TRI0+1, .. hold identity rows (rhs row TRI0 + b is e_{8b}..e_{8b+7}): their
+// tiles left of column tile b are structurally zero and are neither computed nor stored.  TRI0 < 0: dense rhs.
+template <int WARPS, int GI, int TRI0, class Entry, class Rhs>
 __device__ __forceinline__ CholResult tile_cholesky(double* __restrict__ tiles, const int NT, const int NR,
                                                     const Entry& entry, const Rhs& rhs,
                                                     double* __restrict__ wscratch, const int wid,
@@ -55,7 +55,7 @@ __device__ __forceinline__ CholResult tile_cholesky(double* __restrict__ tiles, 
         return (I < NT) ? tiles + ((size_t)I * (I + 1) / 2 + K) * 64
                         : rhs_base + ((size_t)(I - NT) * NT + K) * 64;
     };
-    auto kstart = [&](int I) -> int { return (TRI && I > NT) ? I - NT - 1 : 0; };
+    auto kstart = [&](int I) -> int { return (TRI0 >= 0 && I >= NT + TRI0) ? I - NT - TRI0 : 0; };
     double prod = 1.0, logacc = 0.0;
     bool ok = true;
 
@@ -199,6 +199,34 @@ struct NllRhs {  // row 0 = y^T, row 1 = 1^T, rows 2..7 = 0
             if (j < n) v0 = 1.0;
             if (j + 1 < n) v1 = 1.0;
         }
+    }
+};
+
+// B fragment of a tile Z stored in operand order, for a product X * Z (no transpose): lane l needs
+// Z[l%4 + 4h][l/4].  Two 8-byte loads; used on the few tiles of an inverted diagonal block.
+__device__ __forceinline__ double2 ld_frag_T(const double* tile, int lane) {
+    const int kk = lane & 3, nn = lane >> 2;
+    double2 v;
+    v.x = tile[tile_pos(kk, nn)];
+    v.y = tile[tile_pos(kk + 4, nn)];
+    return v;
+}
+
+// entries of a (<= 32 x 32) diagonal block read back from tile-packed storage (block factorisation step)
+struct BlockEntry {
+    const double* tiles;
+    int J0;
+    __device__ __forceinline__ void operator()(int i, int j, double& v0, double& v1) const {
+        const unsigned I = J0 + (i >> 3), J = J0 + (j >> 3);
+        const double* t = tiles + (size_t)(I * (I + 1) / 2 + J) * 64u;
+        v0 = __ldcg(t + tile_pos(i & 7, j & 7));
+        v1 = __ldcg(t + tile_pos(i & 7, (j & 7) + 1));
+    }
+};
+struct IdentityRhs {
+    __device__ __forceinline__ void operator()(int rr, int j, double& v0, double& v1) const {
+        v0 = (j == rr) ? 1.0 : 0.0;
+        v1 = (j + 1 == rr) ? 1.0 : 0.0;
     }
 };
 
