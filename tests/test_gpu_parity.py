@@ -426,3 +426,70 @@ def test_fast_path_equals_opaque_loop(K):
     slow = LikeliOptimizer().generate_grid(lambda prm: k._calc_likelihood_opti_exp(np.array(prm)), 1, 8, 5)
     assert fast == slow
     assert torch.cuda.is_available()
+
+
+# ------------------------------------------------------------------------------------------ cross-checks between code paths
+@pytest.mark.parametrize('n', [1, 5, 33, 100, 257, 520])
+def test_rbf_cooperative_solve_ragged_sizes(R_, n):
+    """gaussian kernel -> cooperative-grid Cholesky (macro columns of 32: sizes straddle 8 / 32 boundaries)"""
+    rng = np.random.default_rng(n)
+    X = rng.uniform(0, 10, (n, 3))
+    y = np.sin(X[:, 0]) + 0.05 * X[:, 1] ** 2 - 0.01 * X[:, 2] ** 3
+    r = R_(X, y)
+    r.update_param(1.3, 'gaus')
+    ref = orc.rbf_fit(X, y, 2, 1.3)
+    c = orc.cond2(orc.rbf_matrix(X, 2, 1.3))
+    assert np.max(np.abs(r.get_coeff() - ref)) <= 1e-9 * max(1.0, c / 5e6) * np.max(np.abs(ref))
+    xq = rng.uniform(0, 10, (50, 3))
+    assert np.max(rel(r.predict_batch(xq), orc.rbf_predict(X, ref, 2, 1.3, xq))) < 1e-9 * max(1.0, c / 5e6)
+    assert np.max(np.abs(r.predict_batch(X) - y)) < 1e-7 * max(1.0, c / 5e6)      # interpolation property
+
+
+def test_grid_mode_and_list_mode_agree(K):
+    """the same candidates through the grid entry point (tables of |dx|^p / product-form exp tables) and
+    through the list entry point (ln|dx| table, exp(p ln|dx|)): two independent builds of R"""
+    X, y = workloads.c5_kriging_r3()
+    k = K(X, y)
+    _, _, g = k.likelihood_grid(8, 5)
+    g = g.cpu().numpy()
+    e, q = orc.grid_candidates(2, 8, 5)
+    b = k.likelihood_batch(e, q)
+    cond = np.array([orc.cond2(orc.corr_matrix(X, 10. ** e[c], q[c])) for c in range(0, 1600, 3)])
+    m = cond < 1e8
+    assert np.max(rel(g[::3][m], b[::3][m]) / (tol(cond[m]) / 1e-9)) < 1e-9
+
+
+def test_generic_engine_cross_check(K):
+    """SMB_FORCE_GENERIC=1 routes every likelihood through the generic tile engine (krig_nll.cu): the
+    specialised small-n and large-n kernels must agree with it"""
+    import json
+    import subprocess
+    import sys
+    script = r'''
+import json, os, sys
+import numpy as np
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), 'surrogate-models_b200'))
+from mylibs.kriging import Kriging
+from sm_b200 import workloads
+X, y = workloads.c2_halton64()
+a = Kriging(X, y).likelihood_grid(8, 5)[2].cpu().numpy()
+X3, y3 = workloads.c3_lhs1024(n=300, k=8)
+e, p = workloads.c3_candidates(16, 8)
+b = Kriging(X3, y3).likelihood_batch(e, p)
+print(json.dumps(dict(a=[None if not np.isfinite(v) else float(v) for v in a], b=[float(v) for v in b])))
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    for flag in ('0', '1'):
+        env = dict(os.environ, SMB_FORCE_GENERIC=flag)
+        r = subprocess.run([sys.executable, '-c', script], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[flag] = json.loads(r.stdout.strip().split('\n')[-1])
+    g = np.load(os.path.join(GOLD, 'c2_halton64_default_grid.npz'))
+    cond = g['cond']
+    a0 = np.array([np.nan if v is None else v for v in out['0']['a']])
+    a1 = np.array([np.nan if v is None else v for v in out['1']['a']])
+    m = np.isfinite(a0) & np.isfinite(a1) & (cond < 1e8)
+    assert m.sum() > 1000
+    assert np.all(rel(a0[m], a1[m]) <= tol(cond[m]))
+    assert np.max(rel(np.array(out['0']['b']), np.array(out['1']['b']))) < 1e-10   # n = 300 list mode, cond ~1e4
