@@ -44,6 +44,16 @@ def flops_like(n, k):
     return n ** 3 / 3.0 + (k + 2) * n ** 2
 
 
+def measured_traffic():
+    """DRAM bytes of the dominant kernel per launch, from one `ncu --set full` capture of the same launch
+    (profiles/r01_nll_small_traffic.json); None if the record is absent"""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r01_nll_small_traffic.json')) as f:
+            return json.load(f)['traffic_bytes_per_launch']
+    except Exception:
+        return None
+
+
 def fp64_peaks():
     """measured fp64 peaks of this pool's B200 (tools/fp64_peaks.cu -> profiles/r01_fp64_peaks.json);
     MEASURED_PEAKS.json carries HBM and bf16 only"""
@@ -258,8 +268,9 @@ def run_gpu(args):
     t_bound = fl / (peak_tf * 1e12) + n_exp / (exp_gops * 1e9)
     roofline = {
         'bound': 'tensor', 'bound_detail': 'fp64 pipe (DMMA / DFMA share one 37 TFLOP/s peak); not HBM',
-        'kernel': 'krig_nll_small_kernel<8,2,0>', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
-        'frac': achieved / peak_tf, 'peak_source': peak_src, 'traffic': None,
+        'kernel': 'krig_nll_small_kernel<8,2,2>', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
+        'frac': achieved / peak_tf, 'peak_source': peak_src, 'traffic': measured_traffic() if world == 1 else None,
+        'traffic_unit': 'bytes of DRAM traffic per launch (ncu); algorithmic bytes = 8 per candidate + tables once',
         'flops_per_eval': flops_like(N_SAMPLES, K_DIM), 'exp_per_eval': N_SAMPLES * (N_SAMPLES - 1) / 2,
         'kernel_ms': kernel_ms, 'frac_two_resource': t_bound / (kernel_ms * 1e-3),
         'hbm_gbs_achieved': (8.0 * CAND_PER_GPU) / (kernel_ms * 1e-3) / 1e9,
