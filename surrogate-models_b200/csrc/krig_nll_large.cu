@@ -381,6 +381,10 @@ cudaError_t launch_nll_large(NllArgs a, int mode, cudaStream_t st) {
     if (per_sm < 1) per_sm = 1;
     long long grid = (long long)sm_count() * per_sm;
     if (grid > a.C) grid = a.C;
+    // one tile workspace per resident CTA: keep the total under 24 GB (n = 4096: 67 MB each) so very large n
+    // degrades to fewer candidates in flight instead of exhausting HBM
+    const long long ws_cap = (long long)(((size_t)24 << 30) / tile_bytes);
+    if (grid > ws_cap) grid = ws_cap > 0 ? ws_cap : 1;
     double* ws = nullptr;
     e = cudaMallocAsync((void**)&ws, (size_t)grid * tile_bytes, st);
     if (e != cudaSuccess) return e;

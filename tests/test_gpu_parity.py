@@ -493,3 +493,25 @@ print(json.dumps(dict(a=[None if not np.isfinite(v) else float(v) for v in a], b
     assert m.sum() > 1000
     assert np.all(rel(a0[m], a1[m]) <= tol(cond[m]))
     assert np.max(rel(np.array(out['0']['b']), np.array(out['1']['b']))) < 1e-10   # n = 300 list mode, cond ~1e4
+
+
+def test_large_n_and_large_k(K):
+    """n = 2048 (macro-panel kernel, 17 MB of tiles per candidate) and k = 16 (SM_KMAX) against the oracle"""
+    rng = np.random.default_rng(2048)
+    X = rng.uniform(0, 1, (2048, 3))
+    y = np.sin(3 * X.sum(axis=1)) + X[:, 0] ** 2
+    e = np.array([[0.5, 0.8, 0.3], [1.0, 0.2, 0.7], [0.0, 0.0, 0.0]])
+    p = np.array([[1.3, 1.6, 1.1], [1.0, 1.9, 1.5], [1.2, 1.2, 1.2]])
+    k = K(X, y)
+    nll = k.likelihood_batch(e, p)
+    ref = np.array([orc.nll_chol(X, y, 10. ** e[c], p[c]) for c in range(3)])
+    cond = np.array([orc.cond2(orc.corr_matrix(X, 10. ** e[c], p[c])) for c in range(3)])
+    assert check_values(nll, ref, cond, cond_max=1e12) == 3
+    X16 = rng.uniform(0, 1, (150, 16))
+    y16 = np.cos(X16.sum(axis=1))
+    e16, p16 = rng.uniform(-1.5, 0.0, (6, 16)), rng.uniform(1, 2, (6, 16))
+    k16 = K(X16, y16)
+    nll16 = k16.likelihood_batch(e16, p16)
+    ref16 = np.array([orc.nll_chol(X16, y16, 10. ** e16[c], p16[c]) for c in range(6)])
+    cond16 = np.array([orc.cond2(orc.corr_matrix(X16, 10. ** e16[c], p16[c])) for c in range(6)])
+    assert check_values(nll16, ref16, cond16, cond_max=1e12) == 6
