@@ -515,3 +515,23 @@ def test_large_n_and_large_k(K):
     ref16 = np.array([orc.nll_chol(X16, y16, 10. ** e16[c], p16[c]) for c in range(6)])
     cond16 = np.array([orc.cond2(orc.corr_matrix(X16, 10. ** e16[c], p16[c])) for c in range(6)])
     assert check_values(nll16, ref16, cond16, cond_max=1e12) == 6
+
+
+def test_optimize_grid_end_to_end_r3(gold, K, capsys):
+    """Kriging.optimize('grid') end to end on kriging_r3 (n = 36, k = 2): batched grid, then SciPy SLSQP on
+    single evaluations exactly like the reference (likeli_optimizer.py:37-48).  The optimum sits at
+    cond(R) = 7.6e11 where the reference itself ends ABOVE its grid guess (-111.5028 vs -111.5161), so only
+    loose agreement is meaningful."""
+    g = gold('c5_kriging_r3')
+    k = K(g['X'], g['y'])
+    k.optimize(record_data=True)
+    capsys.readouterr()
+    rec = np.array(k.records)
+    e, q = orc.grid_candidates(2, 8, 5)
+    assert np.array_equal(rec[:1600], np.concatenate([e, q], axis=1))           # grid rows first, in order
+    assert rec.shape[0] > 1600 + 5 and rec.shape[1] == 4
+    assert np.all(rec[:, :2] >= -5 - 1e-6) and np.all(rec[:, :2] <= 5 + 1e-6)
+    assert np.all(rec[:, 2:] >= 1 - 1e-6) and np.all(rec[:, 2:] <= 2 + 1e-6)
+    assert abs(rec.shape[0] - int(g['n_records'])) < 400                          # reference: 1750 evaluations
+    assert k.calc_likelihood() <= float(g['grid_nll'][960]) + 1.0
+    assert np.all(np.isfinite(k._theta)) and np.all(k._theta > 0) and np.all((k._p >= 1 - 1e-9) & (k._p <= 2 + 1e-9))
