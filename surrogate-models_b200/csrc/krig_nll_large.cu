@@ -22,7 +22,7 @@
 
 namespace smb {
 
-constexpr int LW = 8;   // warps per CTA
+// warps per CTA LW is a template parameter: 16 / LW CTAs are resident per SM (128 registers per thread)
 constexpr int MB = 4;   // tile columns per macro column
 constexpr int STAGES = 3;  // operand ring depth (k-steps in flight per warp); 2 CTAs x 8 warps x 3 x 4 KB = 192 KB
 
@@ -140,7 +140,8 @@ __device__ __forceinline__ bool diag_factor_plain(double c0, double c1, double* 
     return ok;
 }
 
-__global__ void __launch_bounds__(LW * 32, 2) krig_nll_large_kernel(const NllArgs a, const int mode) {
+template <int LW>
+__global__ void __launch_bounds__(LW * 32, 16 / LW) krig_nll_large_kernel(const NllArgs a, const int mode) {
     __shared__ double etab[EXP_TAB];
     __shared__ double th_s[KMAX], pw_s[KMAX];
     __shared__ long long off_s[KMAX];
@@ -365,18 +366,19 @@ __global__ void __launch_bounds__(LW * 32, 2) krig_nll_large_kernel(const NllArg
     }
 }
 
-// n > 128: macro-panel kernel on a global workspace.  Returns cudaErrorNotSupported for smaller n.
-cudaError_t launch_nll_large(NllArgs a, int mode, cudaStream_t st) {
+// Measured (profiles/r01_nll_large_phases.md): every (LW, CTAs/SM) split lands within ~20 % of the others --
+// many candidates in flight overflow L2 with their tile workspaces (DRAM-latency loads), few leave too little
+// parallelism.  LW = 4 is best up to n = 384, LW = 8 beyond.
+template <int LW>
+static cudaError_t launch_large_t(NllArgs a, int mode, cudaStream_t st) {
     const int NT = a.npad / 8;
-    // n <= 128 stays on the shared-memory tile engine (measured: 2.65 vs 2.25 TFLOP/s at n = 128)
-    if (NT <= 16) return cudaErrorNotSupported;
-    if (a.C <= 0) return cudaSuccess;
     const size_t tile_bytes = chol_tiles(NT, 1) * 512;
     const size_t smem = (size_t)a.npad * 8 + (size_t)LW * STAGES * 8 * 512;
-    cudaError_t e = cudaFuncSetAttribute(krig_nll_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(krig_nll_large_kernel<LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    int per_sm = 1;  // resident CTAs per SM (register-limited)
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, krig_nll_large_kernel, LW * 32, smem);
+    cudaFuncSetAttribute(krig_nll_large_kernel<LW>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    int per_sm = 1;  // resident CTAs per SM (register / shared-memory limited)
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, krig_nll_large_kernel<LW>, LW * 32, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     long long grid = (long long)sm_count() * per_sm;
@@ -389,12 +391,20 @@ cudaError_t launch_nll_large(NllArgs a, int mode, cudaStream_t st) {
     e = cudaMallocAsync((void**)&ws, (size_t)grid * tile_bytes, st);
     if (e != cudaSuccess) return e;
     a.workspace = ws;
-    {
-        krig_nll_large_kernel<<<(int)grid, LW * 32, smem, st>>>(a, mode);
-        e = cudaGetLastError();
-    }
+    krig_nll_large_kernel<LW><<<(int)grid, LW * 32, smem, st>>>(a, mode);
+    e = cudaGetLastError();
     cudaError_t e2 = cudaFreeAsync(ws, st);
     return e != cudaSuccess ? e : e2;
+}
+
+// n > 128: macro-panel kernel on a global workspace.  Returns cudaErrorNotSupported for smaller n.
+cudaError_t launch_nll_large(NllArgs a, int mode, cudaStream_t st) {
+    const int NT = a.npad / 8;
+    // n <= 128 stays on the shared-memory tile engine (measured: 2.65 vs 2.25 TFLOP/s at n = 128)
+    if (NT <= 16) return cudaErrorNotSupported;
+    if (a.C <= 0) return cudaSuccess;
+    if (NT <= 48) return launch_large_t<4>(a, mode, st);
+    return launch_large_t<8>(a, mode, st);
 }
 
 }  // namespace smb
