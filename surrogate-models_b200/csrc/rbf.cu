@@ -375,7 +375,7 @@ cudaError_t launch_rbf_fit(const double* X, const double* y, int n, int k, int k
 
 // ------------------------------------------------------------------------------------ evaluation
 // Samples + coefficients are staged through shared memory in chunks; each thread owns one query.
-constexpr int RBF_CHUNK = 2048;
+constexpr int RBF_CHUNK = 1024;  // samples staged per pass (32 KB at k = 3: 6 CTAs per SM)
 template <int KD>
 __global__ void __launch_bounds__(256) rbf_predict_kernel(const double* __restrict__ X, int n, int k, int kind, double a,
                                                           const double* __restrict__ coeff,
@@ -428,7 +428,8 @@ cudaError_t launch_rbf_predict(const double* X, int n, int k, int kind, double a
     if (Nq <= 0) return cudaSuccess;
     const size_t smem = (size_t)RBF_CHUNK * (k + 1) * 8;
     long long grid = (Nq + 255) / 256;
-    const long long cap = (long long)sm_count() * 4;
+    const long long per_sm = (long long)((size_t)(227 * 1024) / (smem + 1024));  // resident CTAs (shared-memory bound)
+    const long long cap = (long long)sm_count() * (per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm));
     if (grid > cap) grid = cap;
     cudaError_t e;
 #define SMB_RBF_LAUNCH(KD)                                                                                          \
