@@ -245,6 +245,30 @@ def gen_c5():
          opt_cond=orc.cond2(orc.corr_matrix(X, kk._theta, kk._p)))
 
 
+def gen_validation():
+    """mylibs/validation.py of the reference on the kriging_r3 data: fixed-parameter Kriging for the error
+    measures, gaussian RBF for PRESS (its train() is a no-op, so PRESS is deterministic)."""
+    from mylibs.validation import Validation
+    e6 = [0., 2., 4., 6., 8., 10.]
+    px, py, pz = generate_sample_data(f_3d, e6, e6)
+    X = np.array([px, py]).T
+    y = np.array(pz)
+    rng = np.random.default_rng(21)
+    vx = rng.uniform(0, 10, (40, 2))
+    vy = np.array([f_3d(v) for v in vx])
+    k = Kriging(X, y)
+    k.update_param([0.05, 0.05], [1.9, 1.9])
+    v = Validation()
+    r = RBF(X, y)
+    r.update_param(1.0, 'gaus')
+    save('validation_r3', X=X, y=y, vx=vx, vy=vy,
+         krig_deviation=v.calc_deviation(vx, vy, k.predict), krig_rmse=v.calc_rmse(vx, vy, k.predict),
+         krig_mae=v.calc_mae(vx, vy, k.predict), krig_rae=v.calc_rae(vx, vy, k.predict),
+         rbf_rmse=v.calc_rmse(vx, vy, r.predict), rbf_press=v.calc_press(X, y, r.predict, RBF, update_params=[1.0, 'gaus']),
+         halton_7x3=np.array(Halton().generate_sample_plan(7, 3, [(0., 1.), (-1., 1.), (2., 5.)])),
+         structured_9x2=np.array(StructuredSample().generate_sample_plan(9, 2, [(0., 10.), (-5., 5.)])))
+
+
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
     ap.add_argument('--full-c2', action='store_true')
@@ -252,7 +276,7 @@ if __name__ == '__main__':
     ap.add_argument('--procs', type=int, default=os.cpu_count())
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
-    todo = dict(c1=gen_c1, c2=gen_c2_default, c3=gen_c3, c4=gen_c4, c5=gen_c5)
+    todo = dict(c1=gen_c1, c2=gen_c2_default, c3=gen_c3, c4=gen_c4, c5=gen_c5, val=gen_validation)
     if a.full_c2:
         gen_c2_full(a.procs)
     else:

@@ -535,3 +535,29 @@ def test_optimize_grid_end_to_end_r3(gold, K, capsys):
     assert abs(rec.shape[0] - int(g['n_records'])) < 400                          # reference: 1750 evaluations
     assert k.calc_likelihood() <= float(g['grid_nll'][960]) + 1.0
     assert np.all(np.isfinite(k._theta)) and np.all(k._theta > 0) and np.all((k._p >= 1 - 1e-9) & (k._p <= 2 + 1e-9))
+
+
+def test_validation_protocol_against_reference(gold, K, R_):
+    """mylibs.validation (the caller that defines the drop-in protocol, validation.py:96-108) driving the
+    B200 surrogates, against the reference's own Validation driving the reference surrogates"""
+    from mylibs.validation import Validation
+    g = gold('validation_r3')
+    X, y, vx, vy = g['X'], g['y'], g['vx'], g['vy']
+    v = Validation()
+    k = K(X, y)
+    k.update_param([0.05, 0.05], [1.9, 1.9])
+    assert rel(v.calc_deviation(vx, vy, k.predict), g['krig_deviation']) < 1e-9
+    assert rel(v.calc_rmse(vx, vy, k.predict), g['krig_rmse']) < 1e-9
+    assert rel(v.calc_mae(vx, vy, k.predict), g['krig_mae']) < 1e-9
+    assert np.max(np.abs(v.calc_rae(vx, vy, k.predict) - g['krig_rae'])) < 1e-9
+    r = R_(X, y)
+    r.update_param(1.0, 'gaus')
+    assert rel(v.calc_rmse(vx, vy, r.predict), g['rbf_rmse']) < 1e-9
+    assert rel(v.calc_press(X, y, r.predict, R_, update_params=[1.0, 'gaus']), g['rbf_press']) < 1e-9
+    full = v.run_full_analysis(vx, vy, X, y, vx, vy, r.predict, R_, update_params=[1.0, 'gaus'])
+    assert rel(full.press, g['rbf_press']) < 1e-9 and rel(full.rmse, g['rbf_rmse']) < 1e-9
+
+    class NoTrain:                       # a surrogate class without train(): the reference's warning + 0
+        def __init__(self, x, fx):
+            pass
+    assert v.calc_press(X, y, r.predict, NoTrain) == 0.

@@ -144,3 +144,27 @@ def test_shard_range_and_first_min_pairs():
     assert dist.first_min_pairs([3., 1., 1., float('nan')], [5, 9, 7, 0]) == (1., 7)
     assert dist.first_min_pairs([float('inf'), float('inf')], [-1, -1]) == (float('inf'), -1)
     assert dist.rank_world() == (0, 1)
+
+
+def test_sampler_mirrors_bit_identical(gold):
+    from mylibs.halton import Halton
+    from mylibs.structured_sample import StructuredSample
+    g = gold('validation_r3')
+    assert np.array_equal(np.array(Halton().generate_sample_plan(7, 3, [(0., 1.), (-1., 1.), (2., 5.)])), g['halton_7x3'])
+    assert np.array_equal(np.array(StructuredSample().generate_sample_plan(9, 2, [(0., 10.), (-5., 5.)])), g['structured_9x2'])
+    assert Halton().prime(0) == 2 and Halton().prime(3) == 7
+
+
+def test_validation_with_opaque_callable(gold):
+    """Validation on an arbitrary callable follows the reference's per-point path"""
+    from mylibs.validation import Validation, ValidationResults
+    g = gold('validation_r3')
+    f = lambda x: float(np.sin(x[0]) + 0.05 * x[1] ** 2)   # noqa: E731
+    v = Validation()
+    vx, vy = g['vx'], g['vy']
+    pred = np.array([f(x) for x in vx])
+    assert abs(v.calc_rmse(vx, vy, f) - np.sqrt(np.mean((vy - pred) ** 2))) < 1e-14
+    assert abs(v.calc_mae(vx, vy, f) - np.max(np.abs(vy - pred))) < 1e-14
+    assert abs(v.calc_deviation(vx, vy, f) - np.mean(np.abs(vy - pred)) / vy.mean()) < 1e-14
+    assert np.allclose(v.calc_rae(vx, vy, f), np.abs((vy - pred) / vy), rtol=0, atol=1e-14)
+    assert ValidationResults().press == 0.
