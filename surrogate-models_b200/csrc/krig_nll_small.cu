@@ -16,6 +16,28 @@
 
 namespace smb {
 
+#ifdef SMB_PHASE_TIMING
+__device__ unsigned long long g_small_phase[8];
+#define SPH_BEGIN() long long _sp_t = clock64()
+#define SPH_MARK(slot)                                                                              \
+    do {                                                                                            \
+        const long long _n = clock64();                                                             \
+        if (lane == 0 && blockIdx.x == 0 && wid == 0) g_small_phase[slot] += (unsigned long long)(_n - _sp_t); \
+        _sp_t = _n;                                                                                 \
+    } while (0)
+extern "C" int smb_small_phase_read(unsigned long long* out, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_small_phase, sizeof(unsigned long long) * 8);
+    if (e == cudaSuccess && reset) {
+        static unsigned long long z[8];
+        e = cudaMemcpyToSymbol(g_small_phase, z, sizeof(z));
+    }
+    return (int)e;
+}
+#else
+#define SPH_BEGIN()
+#define SPH_MARK(slot)
+#endif
+
 // swizzled operand order: 16-byte chunk index XOR ((row >> 1) & 1): accumulator-fragment stores (2 x STS.64
 // per lane) then hit every bank exactly twice, operand loads stay one conflict-free LDS.128 per lane.
 // The per-lane offsets are computed once per thread (LaneOff) -- recomputing them per access was ~9% of
@@ -104,30 +126,42 @@ __device__ __forceinline__ bool diag_factor(double c0, double c1, double* __rest
     ts[(2 * q + 1) * 8 + r] = c1;
     tp = 1.0;
     double lrw_prev = 0.0;
-    // operand-order positions of W[row][2q], W[row][2q+1] for row = r: used for the store (row = r == j)
-    // and, with row = j, for the delayed read
     const int chq = (2 * q) & 3;
+    // The pivot is the only value on the serial critical chain.  It comes straight from the register that
+    // holds the updated diagonal element (one shuffle); the column / W-row broadcasts through shared memory
+    // are issued BEFORE the reciprocal chain of the step so their latency hides behind it.  (First profile of
+    // this routine: 354 cycles per step -- each dependent fp64 instruction also queues behind the other
+    // warps' DMMAs on the shared pipe, so the chain is kept as short as possible.)
+    double d = __shfl_sync(0xffffffffu, c0, 0);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        __syncwarp();
-        if (j > 0) {  // delayed W update with row j-1 (final since the previous step)
+        __syncwarp();  // column j of ts and row j-1 of wt are visible
+        double wj0 = 0.0, wj1 = 0.0;
+        if (j > 0) {
             const int sj = ((j - 1) >> 1) & 1;
-            const double wj0 = wt[8 * (j - 1) + 2 * (chq ^ sj) + (q >> 1)];
-            const double wj1 = wt[8 * (j - 1) + 2 * ((chq + 1) ^ sj) + (q >> 1)];
-            if (r > j - 1) {
-                w0 = fma(-lrw_prev, wj0, w0);
-                w1 = fma(-lrw_prev, wj1, w1);
-            }
+            wj0 = wt[8 * (j - 1) + 2 * (chq ^ sj) + (q >> 1)];
+            wj1 = wt[8 * (j - 1) + 2 * ((chq + 1) ^ sj) + (q >> 1)];
         }
-        const double d = ts[j * 8 + j];
         const double vr = ts[j * 8 + r];
         const double2 vc = *reinterpret_cast<const double2*>(ts + j * 8 + 2 * q);
+        // 1/d and 1/sqrt(d) from one fp32 seed y ~ d^-1/2 (rel. error e/2, e = 1 - d y^2 ~ 1e-7):
+        //   1/d = y^2 (1 + e + e^2) + O(e^3),   1/sqrt(d) = y (1 + e/2 + 3 e^2 / 8) + O(e^3)
         ok = ok && (d > 1e-36);  // below that R is numerically singular (and the fp32 seed would underflow)
         tp *= d;
-        const double inv = rsqrt_pivot(d);
-        const double t = vr * (inv * inv);
+        const double y = (double)rsqrtf((float)d);
+        const double y2 = y * y;
+        const double e = fma(-d, y2, 1.0);
+        const double inv2 = fma(y2, fma(e, e, e), y2);
+        const double t = vr * inv2;
         c0 = fma(-t, vc.x, c0);
         c1 = fma(-t, vc.y, c1);
+        if (j < 7) d = __shfl_sync(0xffffffffu, ((j + 1) & 1) ? c1 : c0, 4 * (j + 1) + ((j + 1) >> 1));
+        // everything below is off the critical chain
+        const double inv = fma(y, e * fma(0.375, e, 0.5), y);
+        if (j > 0 && r > j - 1) {  // delayed rank-1 update of W with row j-1 (final since the previous step)
+            w0 = fma(-lrw_prev, wj0, w0);
+            w1 = fma(-lrw_prev, wj1, w1);
+        }
         lrw_prev = vr * inv;  // L[r][j]
         if (r == j) {         // row j of W is final: scale and publish in operand order
             wt[8 * r + 2 * (chq ^ s) + (q >> 1)] = w0 * inv;
@@ -195,6 +229,8 @@ __global__ void __launch_bounds__(256, 2) krig_nll_small_kernel(const NllArgs a)
         }
         double prod = 1.0;
         bool ok = true;
+        SPH_BEGIN();
+        SPH_MARK(0);
 
         for (int J = 0; J < NT; ++J) {
             const int cnt = NT - J;  // matrix tiles in this block column: I = J + g, g < cnt (g = 0: diagonal)
@@ -215,6 +251,12 @@ __global__ void __launch_bounds__(256, 2) krig_nll_small_kernel(const NllArgs a)
                     // table entries of the chunk's first tile pair: in flight during the DMMA loop
                     double2 tq[2][KD];
                     load_pair<KD>(P, (J + g0) * 8 * npad + col_off, (J + (g0 + 1 < cnt ? g0 + 1 : g0)) * 8 * npad + col_off, tq);
+                    double2 tn[2][KD];
+                    const bool second = (g0 + 2 < NTM) && (g0 + 2 < cnt);
+                    if (MODE == 2 && second) {  // product form: nothing to overlap the second pair with later
+                        const int g3 = (g0 + 3 < cnt) ? g0 + 3 : g0 + 2;
+                        load_pair<KD>(P, (J + g0 + 2) * 8 * npad + col_off, (J + g3) * 8 * npad + col_off, tn);
+                    }
                     for (int K = 0; K < J; ++K) {
                         // operands first (independent LDS), then every first k-half, then every second k-half
                         const double2 b = ld_frag_sw(rowJ + K * 64, lo);
@@ -242,11 +284,10 @@ __global__ void __launch_bounds__(256, 2) krig_nll_small_kernel(const NllArgs a)
                             if (g0 + gg < NTM && g0 + gg < cnt) dmma(acc[gg][0], acc[gg][1], av[gg].y, b.y);
                         if (g0 == 0) dmma(accr[0], accr[1], a1, b.y);
                     }
+                    SPH_MARK(1);
                     // correlation entries, two tiles (4 exp per lane) at a time; the second pair's table
                     // entries are requested before the first pair is evaluated
-                    double2 tn[2][KD];
-                    const bool second = (g0 + 2 < NTM) && (g0 + 2 < cnt);
-                    if (second) {
+                    if (MODE != 2 && second) {
                         const int g3 = (g0 + 3 < cnt) ? g0 + 3 : g0 + 2;
                         load_pair<KD>(P, (J + g0 + 2) * 8 * npad + col_off, (J + g3) * 8 * npad + col_off, tn);
                     }
@@ -265,6 +306,7 @@ __global__ void __launch_bounds__(256, 2) krig_nll_small_kernel(const NllArgs a)
                         acc[3][0] = u0 - acc[3][0];
                         acc[3][1] = u1 - acc[3][1];
                     }
+                    SPH_MARK(2);
                     // park the un-normalised panel tiles in their final slots (accumulator -> operand layout)
 #pragma unroll
                     for (int gg = 0; gg < 4; ++gg) {
@@ -288,11 +330,13 @@ __global__ void __launch_bounds__(256, 2) krig_nll_small_kernel(const NllArgs a)
                     rhs_s[J * 16 + r * 8 + 2 * q + 1] = y1 - accr[1];
                 }
             }
+            SPH_MARK(3);
             // ------------------------------------------------------------ D: diagonal tile
             double tp;
             ok = diag_factor(dc0, dc1, dscr, wscr, tp, lane) && ok;  // ends with __syncwarp
             if (!ok) break;  // warp-uniform
             if (lane == J) prod = tp;  // NT <= 8: lane J keeps the pivot product of tile J
+            SPH_MARK(4);
             // ------------------------------------------------------------ T: L_IJ = C_IJ W^T
             const double2 wf = ld_frag_sw(wscr, lo);
 #pragma unroll
@@ -338,6 +382,7 @@ __global__ void __launch_bounds__(256, 2) krig_nll_small_kernel(const NllArgs a)
                 }
             }
             __syncwarp();
+            SPH_MARK(5);
         }
         // ---------------------------------------------------------------- epilogue
         double nll = INFINITY;
@@ -362,6 +407,7 @@ __global__ void __launch_bounds__(256, 2) krig_nll_small_kernel(const NllArgs a)
         }
         if (lane == 0) a.nll_out[c] = nll;
         __syncwarp();
+        SPH_MARK(6);
     }
 }
 
