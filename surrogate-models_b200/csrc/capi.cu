@@ -141,7 +141,9 @@ int sm_krig_nll_batch(const double* X, const double* y, int n, int k, const doub
     const int npad = sm_krig_npad(n);
     DevBuf lg(st), nll_tmp(st);
     SM_TRY(lg.alloc((size_t)npad * npad * k * 8));
-    SM_TRY(launch_logtab(X, n, k, npad, lg.as<double>(), st));
+    const bool flow = nll_uses_flow(n);  // n > 128: base-2 table for the dataflow kernel
+    if (flow) SM_TRY(launch_log2tab(X, n, k, npad, lg.as<double>(), st));
+    else SM_TRY(launch_logtab(X, n, k, npad, lg.as<double>(), st));
     L.n += 1;
     if (!nll_out) {
         SM_TRY(nll_tmp.alloc((size_t)C * 8));
@@ -150,7 +152,9 @@ int sm_krig_nll_batch(const double* X, const double* y, int n, int k, const doub
     NllArgs a{};
     a.X = X; a.y = y; a.n = n; a.k = k; a.npad = npad;
     a.C = C; a.c_begin = idx_base;
-    a.theta = theta; a.p = p; a.logtab = lg.as<double>();
+    a.theta = theta; a.p = p;
+    if (flow) a.log2tab = lg.as<double>();
+    else a.logtab = lg.as<double>();
     a.nll_out = nll_out;
     SM_TRY(launch_nll(a, 1, st, &L.n));
     if (best_val && best_idx) {

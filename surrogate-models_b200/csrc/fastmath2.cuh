@@ -1,0 +1,63 @@
+// Base-2 table-driven exponentials for the large-n correlation build (krig_nll_flow.cu).
+//
+// List mode needs |dx|^p per (entry, dimension, candidate) -- 9 exponentials per matrix entry at k = 8, more
+// fp64-pipe time than the Cholesky itself at n = 256.  Working in base 2 with a pre-scaled log table removes
+// the range-reduction multiplies of exp():
+//   table  L2S = 512 log2|dx|  (power-of-two scaling: exact)
+//   t  = fma(p, L2S, MAGIC)        low word of t = N = round(512 p log2|dx|)
+//   r  = fma(p, L2S, -(t - MAGIC)) exact residual in units of 1/512 (one rounding), |r| <= 1/2
+//   |dx|^p = 2^(N >> 9) * T[N & 511] * 2^(r / 512),   T[j] = 2^(j/512) (4 KB in shared memory)
+//   2^(r/512) - 1 by a degree-4 polynomial in r (|r ln2/512| <= 6.8e-4: truncation 1.2e-18 relative)
+// 9 fp64-pipe instructions per power (exp_unguarded of fastmath.cuh: 12 + the p * ln|dx| multiply) and the
+// accumulation s += theta' * |dx|^p is one more fma (theta' = theta * log2 e, so R = 2^(-s)).
+// Checked against long-double libm on the host (tests/test_host_logic.py::test_exp2_core_emulation builds
+// tools/exp2_check.c from the same constants): max 0.52 ulp + the rounding of the table argument.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace smb {
+
+constexpr int E2TAB = 512;
+constexpr double E2_CLAMP = 430.0 * 512.0;  // |L2S| <= this: p in [0, 2.3] keeps 2^(p log2|dx|) a normal number
+
+// (ln2/512)^k / k!
+#define SMB_E2_C1 1.3538030870311431e-03
+#define SMB_E2_C2 9.163913992275266e-07
+#define SMB_E2_C3 4.135378350676714e-10
+#define SMB_E2_C4 1.399621994296973e-13
+
+// t = MAGIC + N (N in the low word), r = residual in units of 1/512 log2
+__device__ __forceinline__ double exp2_core(double t, double r, const double* __restrict__ tab) {
+    const int N = __double2loint(t);
+    double q = SMB_E2_C4;
+    q = fma(q, r, SMB_E2_C3);
+    q = fma(q, r, SMB_E2_C2);
+    q = fma(q, r, SMB_E2_C1);
+    const double e = q * r;
+    const double T = tab[N & (E2TAB - 1)];
+    const double v = fma(T, e, T);
+    return __hiloint2double(__double2hiint(v) + ((N >> 9) << 20), __double2loint(v));
+}
+
+// |dx|^p from l2s = 512 log2|dx| (clamped to +-E2_CLAMP); valid without guards for p in [0, 2.3]
+__device__ __forceinline__ double pow2_fast(double p, double l2s, const double* __restrict__ tab) {
+    const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52
+    const double t = fma(p, l2s, MAGIC);
+    const double nf = t - MAGIC;
+    const double r = fma(p, l2s, -nf);
+    return exp2_core(t, r, tab);
+}
+
+// 2^(-s); s >= 0 in the correlation build.  Results below 2^-1021 are flushed to 0, NaN propagates.
+__device__ __forceinline__ double exp2_neg(double s, const double* __restrict__ tab) {
+    const double MAGIC = 6755399441055744.0;
+    const double t = fma(s, -512.0, MAGIC);
+    const double nf = t - MAGIC;
+    const double r = fma(s, -512.0, -nf);
+    double v = exp2_core(t, r, tab);
+    v = (s > 1021.0) ? 0.0 : v;
+    v = (s < -1023.0) ? INFINITY : v;
+    return v;
+}
+
+}  // namespace smb

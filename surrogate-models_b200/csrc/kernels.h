@@ -22,7 +22,8 @@ struct NllArgs {
     // list mode (MODE 1)
     const double* theta;  // [C][k] linear
     const double* p;      // [C][k]
-    const double* logtab;  // [k][npad][npad]
+    const double* logtab;  // [k][npad][npad]  ln|dx| (n <= 128 kernels)
+    const double* log2tab;  // [k][npad][npad]  512 log2|dx| (krig_nll_flow.cu, n > 128)
     // output / scratch
     double* nll_out;    // [C]
     double* workspace;  // tile storage for the global-memory variant
@@ -41,6 +42,9 @@ size_t nll_smem_bytes(int npad, int slots, int nwarps, size_t tile_bytes);
 cudaError_t launch_nll(NllArgs a, int mode, cudaStream_t st, long long* launches);
 cudaError_t launch_nll_small(const NllArgs& a, int mode, cudaStream_t st);
 cudaError_t launch_nll_large(NllArgs a, int mode, cudaStream_t st);
+cudaError_t launch_nll_flow(NllArgs a, int mode, cudaStream_t st);
+bool nll_uses_flow(int n);
+cudaError_t launch_log2tab(const double* X, int n, int k, int npad, double* LG, cudaStream_t st);
 cudaError_t launch_dtab(const double* X, int n, int k, int npad, const double* p_axis, int P, double* D, cudaStream_t st);
 cudaError_t launch_egrid(const double* dtab, const double* theta_axis, int k, int P, int T, int npad, double* E, cudaStream_t st);
 cudaError_t launch_logtab(const double* X, int n, int k, int npad, double* LG, cudaStream_t st);

@@ -330,6 +330,7 @@ cudaError_t launch_nll(NllArgs a, int mode, cudaStream_t st, long long* launches
     if (!force_generic) {
         // n <= 64, k <= 4: warp-per-candidate kernel (krig_nll_small.cu); otherwise the macro-panel kernel
         cudaError_t es = launch_nll_small(a, mode, st);
+        if (es == cudaErrorNotSupported) es = launch_nll_flow(a, mode, st);
         if (es == cudaErrorNotSupported) es = launch_nll_large(a, mode, st);
         if (es != cudaErrorNotSupported) {
             if (launches) *launches += 1;
