@@ -101,8 +101,14 @@ int sm_krig_nll_grid(const double* X, const double* y, int n, int k, const doubl
     Launches L;
     const int npad = sm_krig_npad(n);
     DevBuf dtab(st), nll_tmp(st);
-    SM_TRY(dtab.alloc((size_t)npad * npad * k * P * 8));
-    SM_TRY(launch_dtab(X, n, k, npad, p_axis, P, dtab.as<double>(), st));
+    const bool flow = nll_uses_flow(n);  // n > 128: tile-packed lower-triangle tables for the dataflow kernel
+    if (flow) {
+        SM_TRY(dtab.alloc(flow_table_doubles(n) * k * P * 8));
+        SM_TRY(launch_dtab_packed(X, n, k, npad, p_axis, P, dtab.as<double>(), st));
+    } else {
+        SM_TRY(dtab.alloc((size_t)npad * npad * k * P * 8));
+        SM_TRY(launch_dtab(X, n, k, npad, p_axis, P, dtab.as<double>(), st));
+    }
     L.n += 1;
     if (!nll_out) {
         SM_TRY(nll_tmp.alloc((size_t)c_count * 8));
@@ -140,8 +146,8 @@ int sm_krig_nll_batch(const double* X, const double* y, int n, int k, const doub
     Launches L;
     const int npad = sm_krig_npad(n);
     DevBuf lg(st), nll_tmp(st);
-    SM_TRY(lg.alloc((size_t)npad * npad * k * 8));
-    const bool flow = nll_uses_flow(n);  // n > 128: base-2 table for the dataflow kernel
+    const bool flow = nll_uses_flow(n);  // n > 128: base-2, tile-packed table for the dataflow kernel
+    SM_TRY(lg.alloc((flow ? flow_table_doubles(n) : (size_t)npad * npad) * k * 8));
     if (flow) SM_TRY(launch_log2tab(X, n, k, npad, lg.as<double>(), st));
     else SM_TRY(launch_logtab(X, n, k, npad, lg.as<double>(), st));
     L.n += 1;

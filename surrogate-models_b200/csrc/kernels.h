@@ -27,6 +27,7 @@ struct NllArgs {
     // output / scratch
     double* nll_out;    // [C]
     double* workspace;  // tile storage for the global-memory variant
+    int l2mode;         // krig_nll_flow.cu: L2 eviction policies, 2 bits each: A strips | B strips << 2 | tables << 4
 };
 
 struct NllPlan {
@@ -44,7 +45,9 @@ cudaError_t launch_nll_small(const NllArgs& a, int mode, cudaStream_t st);
 cudaError_t launch_nll_large(NllArgs a, int mode, cudaStream_t st);
 cudaError_t launch_nll_flow(NllArgs a, int mode, cudaStream_t st);
 bool nll_uses_flow(int n);
-cudaError_t launch_log2tab(const double* X, int n, int k, int npad, double* LG, cudaStream_t st);
+cudaError_t launch_log2tab(const double* X, int n, int k, int npad, double* LG, cudaStream_t st);  // tile-packed, [flow_table_doubles(n)][k]
+cudaError_t launch_dtab_packed(const double* X, int n, int k, int npad, const double* p_axis, int P, double* D, cudaStream_t st);
+size_t flow_table_doubles(int n);  // doubles of ONE tile-packed lower-triangle table
 cudaError_t launch_dtab(const double* X, int n, int k, int npad, const double* p_axis, int P, double* D, cudaStream_t st);
 cudaError_t launch_egrid(const double* dtab, const double* theta_axis, int k, int P, int T, int npad, double* E, cudaStream_t st);
 cudaError_t launch_logtab(const double* X, int n, int k, int npad, double* LG, cudaStream_t st);

@@ -1,27 +1,30 @@
-// Large-n batched likelihood kernel (n > 128): one CTA per candidate, tile-packed factor in a per-CTA slice of
-// a global workspace, and NO block barrier inside a candidate -- the warps of the CTA pull tasks from a queue
-// in shared memory and synchronise through progress counters (dataflow), so that
-//   * the latency-bound factorisation of a 32x32 diagonal block runs AHEAD of the bulk updates that do not
-//     depend on it (look-ahead) instead of stalling 8 warps behind 10 barriers per macro column,
-//   * a row group's update, its correlation entries and its panel solve are ONE task: the updated block never
-//     goes back to memory between them,
-//   * work is handed out dynamically, one 32-row group at a time.
-// Same algorithm and results contract as the tile engine (tile_chol.cuh): R = L L^T by 8x8 fp64 tiles on DMMA,
-// right-hand sides y / 1 riding along as tile row NT, nll = n/2 ln sigma^2 + sum ln L_ii, +inf when a pivot
-// is not positive.  Reference semantics: mylibs/kriging.py:53-116,130-141 per candidate.
+// Large-n batched likelihood kernel (n > 128): one CTA per candidate, tile-packed factor in a per-CTA slice of a
+// global workspace, and NO block barrier inside a candidate -- the warps of the CTA pull tasks from a queue in shared
+// memory and synchronise through progress counters (dataflow).  Same algorithm and results contract as the tile
+// engine (tile_chol.cuh): R = L L^T by 8x8 fp64 tiles on DMMA, right-hand sides y / 1 riding along as an extra tile
+// row, nll = n/2 ln sigma^2 + sum ln L_ii, +inf when a pivot is not positive.
+// Reference semantics: mylibs/kriging.py:53-116,130-141 per candidate.
 //
-// Macro column b = tile columns 4b..4b+3 (32 matrix columns).  Row group g = tile rows 4g..4g+3; group NB is
-// the right-hand-side tile row.  Tasks, in queue order
-//     P(0); for b = 0..NB-1:  G(b,b+1), P(b+1), G(b,b+2), ..., G(b,NB-1), G(b,NB)
-//   P(b)    D = R[b,b] - sum_{K<4b} L[b,K] L[b,K]^T (DMMA, lower tiles), then on ONE warp: 32x32 Cholesky with a
-//           lane per row (left-looking, columns broadcast through shared memory), W = D^-1/2 ... = L_bb^-1 by a
-//           lane per column, pivots -> log-determinant.  W goes to shared memory (two slots).
-//           needs: rowdone[b] >= b
-//   G(b,g)  C = R[g,b] - sum_{K<4b} L[g,K] L[b,K]^T (4x4 tiles per warp: 32 DMMAs per 8 operand tiles, operands
-//           through a per-warp cp.async ring), X = C W^T (80 DMMAs, C through the warp's scratch), X -> global.
-//           needs: pdone >= b+1, rowdone[g] >= b
-// Every task's prerequisites precede it in the queue, so a warp that waits is always waiting for a task another
-// warp is already running: no deadlock.
+// Macro column b = tile columns 4b..4b+3 (32 matrix columns).  Row group g = tile rows 4g..4g+3; group NB is the
+// right-hand-side tile row.  Three task types:
+//   E(b,g)  correlation entries R of block (g, b) (g == b: the lower tiles of the diagonal block) -> the block's own
+//           tile slots.  No prerequisites: these tasks are queued one macro column AHEAD of their consumers and
+//           interleaved 1:1 with the update tasks, so (a) the fp64 vector work of the build and the DMMA work of the
+//           updates are in flight on an SM at the same time instead of in alternating phases, (b) the build is off the
+//           critical path P(b) -> U(b,b+1) -> P(b+1) that bounds small n.
+//   P(b)    D = R[b,b] - sum_{K<4b} L[b,K] L[b,K]^T (DMMA, lower tiles), then on ONE warp: 32x32 Cholesky with a lane per
+//           row (left-looking, columns broadcast through shared memory), inverses of the four 8x8 diagonal tiles,
+//           pivots -> log-determinant.  Result (W slot in shared memory): W_jj = L_jj^-1 and -L_jj,m.
+//           needs: rowdone[b] >= b, erow[b] >= b+1
+//   U(b,g)  C = R[g,b] - sum_{K<4b} L[g,K] L[b,K]^T (4x4 tiles per warp: 32 DMMAs per 8 operand tiles, operands through
+//           a per-warp cp.async ring), X = C L_bb^-T by block forward substitution (80 DMMAs, through the warp's
+//           scratch), X -> the block's tile slots.
+//           needs: rowdone[b] >= b, rowdone[g] >= b to start; erow[g] >= b+1 after the k-loop; pdone >= b+1 before
+//           the solve -- so the factorisation of the diagonal block runs in parallel with the updates (look-ahead).
+// Queue:  E(0,0) P(0) E(0,1..NB-1);  then per macro column b:
+//         E(b+1,b+1) U(b,b+1) P(b+1) [U(b,b+j) E(b+1,b+j)]_{j=2..} U(b,NB)
+// Every task's prerequisites precede it in the queue, so a warp that waits is always waiting for a task another warp
+// is already running: no deadlock.
 #include "fastmath.cuh"
 #include "fastmath2.cuh"
 #include "tile_chol.cuh"
@@ -52,22 +55,35 @@ extern "C" int smb_flow_phase_read(unsigned long long* out, int reset) {
 #define FPH_MARK(slot)
 #endif
 
-constexpr int FLOW_MAXG = 258;  // row groups incl. the right-hand-side group: n <= 8192
+constexpr int FLOW_MAXG = 130;  // row groups incl. the right-hand-side group: n <= 4096
 
 __device__ double g_e2tab[E2TAB];  // 2^(j/512), correctly rounded on the host (launch_nll_flow)
 
 struct FlowCtl {
     double etab[E2TAB];
-    double W[2][10 * 64];  // L_bb^-1 of macro column b in slot b & 1: lower tiles (jj, m) at (jj (jj+1)/2 + m) * 64
-    double th2[KMAX];      // theta * log2(e)
-    double pw[KMAX];
-    long long off[KMAX];
-    double logacc;  // sum of ln(pivot) = ln det R
-    int pdone, next_task, failed, pad0;
-    int rowdone[FLOW_MAXG];  // macro columns finished for this row group
-    int coldone[FLOW_MAXG];  // G tasks finished in this macro column
+    double W[2][10 * 64];  // factor of the diagonal block of macro column b in slot b & 1 (see P / U)
+    double th2[KMAX];      // theta * log2(e); 0 beyond k
+    double pw[KMAX];       // 1 beyond k
+    long long off[KMAX];   // table offset of dimension d; beyond k: that of k - 1
+    double inv[32];        // 1 / L_jj of the diagonal block being factored (one P task at a time)
+    double logacc;         // sum of ln(pivot) = ln det R
+    int pdone, next_task, failed, safe_p;
+    int rowdone[FLOW_MAXG];  // macro columns finished (X stored) for this row group
+    int coldone[FLOW_MAXG];  // U tasks finished in this macro column
+    int erow[FLOW_MAXG];     // macro columns whose entries are parked for this row group
 };
 
+// L2 eviction policies: 0 evict_normal, 1 evict_first
+__device__ __forceinline__ unsigned long long make_policy(int kind) {
+    unsigned long long p;
+    if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(p));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;\n" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void fcp_async16(void* smem_dst, const void* gmem_src, unsigned long long pol) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void fcp_async16(void* smem_dst, const void* gmem_src) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
@@ -78,7 +94,7 @@ __device__ __forceinline__ void fcp_wait() { asm volatile("cp.async.wait_group %
 
 __device__ __forceinline__ void wait_ge(const int* p, int v) {
     const volatile int* vp = p;
-    while (*vp < v) __nanosleep(200);
+    while (*vp < v) __nanosleep(100);
     __threadfence_block();
 }
 
@@ -89,69 +105,152 @@ __device__ __noinline__ double pow2_slow(double p, double l2s) {
     return exp2(p * (l2s * (1.0 / 512.0)));
 }
 
-// R entries (i, j), (i, j+1) of this lane.  MODE 0 (grid): tab = |dx|^p tables, off[d] selects (d, q_d);
-// MODE 1 (list): tab = 512 log2|dx|.  Table loads are issued four dimensions at a time, the next chunk before the
-// current one is evaluated.
-template <int MODE>
-struct FlowEntry {
-    const FlowCtl* S;
-    const double* tab;
-    int k, npad;
-    bool safe_p;
-    __device__ __forceinline__ void load4(size_t ij, int d0, double2 (&t)[4]) const {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int d = (d0 + u < k) ? d0 + u : k - 1;
-            t[u] = *reinterpret_cast<const double2*>(tab + S->off[d] + ij);
-        }
-    }
-    __device__ __forceinline__ void operator()(int i, int j, double& v0, double& v1) const {
-        double s0 = 0.0, s1 = 0.0;
-        const size_t ij = (size_t)i * npad + j;
-        double2 cur[4], nxt[4];
-        load4(ij, 0, cur);
-        for (int d0 = 0; d0 < k; d0 += 4) {
-            if (d0 + 4 < k) load4(ij, d0 + 4, nxt);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (d0 + u < k) {  // warp-uniform
-                    double e0 = cur[u].x, e1 = cur[u].y;
-                    if (MODE == 1) {
-                        const double pd = S->pw[d0 + u];
-                        if (safe_p) {
-                            e0 = pow2_fast(pd, e0, S->etab);
-                            e1 = pow2_fast(pd, e1, S->etab);
-                        } else {
-                            e0 = pow2_slow(pd, e0);
-                            e1 = pow2_slow(pd, e1);
-                        }
-                    }
-                    s0 = fma(S->th2[d0 + u], e0, s0);
-                    s1 = fma(S->th2[d0 + u], e1, s1);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) cur[u] = nxt[u];
-        }
-        v0 = exp2_neg(s0, S->etab);
-        v1 = exp2_neg(s1, S->etab);
-    }
+// Workspace of one candidate: (4 NB + 1) tile rows of NT tiles (uniform row stride; only the lower triangle and the
+// right-hand-side row 4 NB are ever touched).  Rows NT .. 4 NB - 1 pad the last row group: they are read as
+// operands of partial groups (garbage in, garbage out into accumulators that are never stored).
+__host__ __device__ inline size_t flow_ws_doubles(int NT) { return (size_t)((NT + 3) / 4 * 4 + 1) * NT * 64; }
+
+struct FlowGeom {
+    int NT, NB, n;
+    unsigned rowstride;  // doubles
+    __device__ __forceinline__ explicit FlowGeom(const NllArgs& a)
+        : NT(a.npad / 8), NB((a.npad / 8 + 3) / 4), n(a.n), rowstride((unsigned)(a.npad / 8) * 64u) {}
+    // doubles from the workspace base; I == 4 NB is the right-hand-side row
+    __device__ __forceinline__ unsigned tile_off(int I, int K) const { return (unsigned)I * rowstride + (unsigned)K * 64u; }
 };
 
+// ---------------------------------------------------------------------------------------------- task E(b, g)
+// Tables are TILE-PACKED in lane order: for the lower tile (I, J), tri = I (I+1)/2 + J, the 64 values of one dimension
+// are contiguous and lane l's pair (8I + l/4, 8J + 2(l%4) [+1]) sits at doubles [2l, 2l+1], so a warp reads a tile of
+// one dimension as ONE coalesced 512-byte request (the row-major table cost 8 separate 64-byte pieces per request).
+//   MODE 1 (list): tab[(tri * k + d) * 64 + 2l] = 512 log2|dx_d|          off[d] = 64 d,  tstride = 64 k
+//   MODE 0 (grid): tab[((d * P + q) * ntri + tri) * 64 + 2l] = |dx_d|^p_q  off[d] selects (d, q_d), tstride = 64
+// A chunk = 4 dimensions x 2 entries is evaluated as ONE straight-line block so the 8 independent powers interleave;
+// the table values of the next two chunks are in flight meanwhile (three register buffers).  Dimensions k .. 4 ceil(k/4)
+// - 1 run with weight 0 (the per-candidate parameter arrays are padded).
+template <int MODE>
+__device__ __forceinline__ void flow_task_e(const FlowCtl& S, const NllArgs& a, double* __restrict__ tiles, const int b,
+                                            const int g, const int lane) {
+    const FlowGeom G(a);
+    const bool diag = (g == b);
+    const int ntile = diag ? 10 : 16;
+    const int nrow = min(4, G.NT - 4 * g), ncol = min(4, G.NT - 4 * b);
+    const double* const tab = (MODE == 0 ? a.dtab : a.log2tab) + 2 * lane;
+    const unsigned tstride = (MODE == 0) ? 64u : 64u * (unsigned)a.k;
+    const int nch = (a.k + 3) >> 2;
+    const bool safe_p = S.safe_p != 0;
+    double* const slots = tiles + 2 * lane;
+
+    auto tile_ij = [&](int e, int& ii, int& jj) {
+        if (diag) {
+            ii = (e >= 6) ? 3 : (e >= 3) ? 2 : (e >= 1) ? 1 : 0;
+            jj = e - ii * (ii + 1) / 2;
+        } else {
+            ii = e >> 2;
+            jj = e & 3;
+        }
+    };
+    int le = 0, lch = 0, ce = 0, cch = 0;  // load / compute cursors (tile, chunk)
+    double s0 = 0.0, s1 = 0.0;
+    auto issue = [&](double2 (&buf)[4]) {
+        if (le < ntile) {
+            int ii, jj;
+            tile_ij(le, ii, jj);
+            const unsigned I = 4 * g + min(ii, nrow - 1), J = 4 * b + min(jj, ncol - 1);  // clamped: always a real tile
+            const double* src = tab + (size_t)(I * (I + 1) / 2 + J) * tstride;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) buf[u] = __ldg(reinterpret_cast<const double2*>(src + S.off[4 * lch + u]));
+            if (++lch == nch) {
+                lch = 0;
+                ++le;
+            }
+        }
+    };
+    auto consume = [&](const double2 (&buf)[4]) {
+        double e0[4], e1[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            e0[u] = buf[u].x;
+            e1[u] = buf[u].y;
+        }
+        if (MODE == 1) {
+            if (safe_p) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const double pd = S.pw[4 * cch + u];
+                    e0[u] = pow2_fast(pd, e0[u], S.etab);
+                    e1[u] = pow2_fast(pd, e1[u], S.etab);
+                }
+            } else {
+#pragma unroll 1
+                for (int u = 0; u < 4; ++u) {
+                    const double pd = S.pw[4 * cch + u];
+                    e0[u] = pow2_slow(pd, e0[u]);
+                    e1[u] = pow2_slow(pd, e1[u]);
+                }
+            }
+        }
+        double t0 = 0.0, t1 = 0.0;  // two partial sums per entry: shorter dependent chains
+#pragma unroll
+        for (int u = 0; u < 4; u += 2) {
+            s0 = fma(S.th2[4 * cch + u], e0[u], s0);
+            s1 = fma(S.th2[4 * cch + u], e1[u], s1);
+            t0 = fma(S.th2[4 * cch + u + 1], e0[u + 1], t0);
+            t1 = fma(S.th2[4 * cch + u + 1], e1[u + 1], t1);
+        }
+        s0 += t0;
+        s1 += t1;
+        if (cch == nch - 1) {
+            int ii, jj;
+            tile_ij(ce, ii, jj);
+            if (ii < nrow && jj < ncol)
+                *reinterpret_cast<double2*>(slots + G.tile_off(4 * g + ii, 4 * b + jj)) =
+                    make_double2(exp2_neg(s0, S.etab), exp2_neg(s1, S.etab));
+            s0 = s1 = 0.0;
+        }
+        if (++cch == nch) {
+            cch = 0;
+            ++ce;
+        }
+    };
+    const int total = ntile * nch;
+    double2 b0[4], b1[4], b2[4];
+    issue(b0);
+    issue(b1);
+#pragma unroll 1
+    for (int x = 0; x < total; x += 3) {
+        issue(b2);
+        consume(b0);
+        if (x + 1 < total) {
+            issue(b0);
+            consume(b1);
+        }
+        if (x + 2 < total) {
+            issue(b1);
+            consume(b2);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- k-loop
 // Accumulate  acc[ii][jj] += sum_{K < nk} A_ii,K * B_jj,K^T  (tiles in operand order, K-th tile of a strip 64 doubles
 // after the previous one).  DIAG: B strip == A strip, lower tiles only.  Operands go through this warp's
 // cp.async ring: every lane copies exactly the 16 bytes it reads back, so a stage needs no warp synchronisation.
+// abase / bbase: tile 0 of the first row of the strip (+ 2 * lane); row ii starts ii * rowstride doubles later.
 template <int HI, bool DIAG, int ST>
-__device__ __forceinline__ void strip_update(double (&acc)[HI][4][2], const double* __restrict__ tiles,
-                                             const unsigned (&aoff)[HI], const unsigned (&boff)[4], const int nk,
-                                             double* __restrict__ ring /* + 2 * lane */) {
+__device__ __forceinline__ void strip_update(double (&acc)[HI][4][2], const double* __restrict__ abase,
+                                             const double* __restrict__ bbase, const unsigned rowstride, const int nk,
+                                             double* __restrict__ ring /* + 2 * lane */, const bool stream_a) {
     auto issue = [&](int K, int stage) {
+        // A strips are read once per macro column: evict_first keeps them from flushing the B strips and the tables
+        // out of L2 (the policy is re-created here instead of living in two registers across the loop)
+        const unsigned long long pol_a = make_policy(stream_a ? 1 : 0);
         double* dst = ring + stage * (8 * 64);
 #pragma unroll
-        for (int ii = 0; ii < HI; ++ii) fcp_async16(dst + ii * 64, tiles + aoff[ii] + (size_t)K * 64);
+        for (int ii = 0; ii < HI; ++ii) fcp_async16(dst + ii * 64, abase + (size_t)(ii * rowstride + K * 64), pol_a);
         if (!DIAG) {
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) fcp_async16(dst + (4 + jj) * 64, tiles + boff[jj] + (size_t)K * 64);
+            for (int jj = 0; jj < 4; ++jj) fcp_async16(dst + (4 + jj) * 64, bbase + (size_t)(jj * rowstride + K * 64));
         }
     };
 #pragma unroll
@@ -159,54 +258,56 @@ __device__ __forceinline__ void strip_update(double (&acc)[HI][4][2], const doub
         if (s < nk) issue(s, s);
         fcp_commit();
     }
-    int st_rd = 0, st_wr = ST - 1;
+    int st_rd = 0;
+#pragma unroll 1
     for (int K = 0; K < nk; ++K) {
+        const int st_wr = (st_rd == 0) ? ST - 1 : st_rd - 1;
         if (K + ST - 1 < nk) issue(K + ST - 1, st_wr);
         fcp_commit();
         fcp_wait<ST - 1>();  // the copies of step K have landed
         const double* src = ring + st_rd * (8 * 64);
-        double2 ca[HI], cb[4];
-#pragma unroll
-        for (int ii = 0; ii < HI; ++ii) ca[ii] = *reinterpret_cast<const double2*>(src + ii * 64);
         if (DIAG) {
+            double2 ca[4];
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) cb[jj] = ca[jj < HI ? jj : 0];
+            for (int ii = 0; ii < 4; ++ii) ca[ii] = *reinterpret_cast<const double2*>(src + ii * 64);
+#pragma unroll
+            for (int ii = 0; ii < HI; ++ii)
+#pragma unroll
+                for (int jj = 0; jj <= ii; ++jj) dmma(acc[ii][jj][0], acc[ii][jj][1], ca[ii].x, ca[jj].x);
+#pragma unroll
+            for (int ii = 0; ii < HI; ++ii)
+#pragma unroll
+                for (int jj = 0; jj <= ii; ++jj) dmma(acc[ii][jj][0], acc[ii][jj][1], ca[ii].y, ca[jj].y);
         } else {
+            // B fragments stay in registers for the step, the A fragment of one tile row at a time (the four DMMAs of a
+            // k-half go to independent accumulators, so the dependent pair x -> y is 64 issue cycles apart)
+            double2 cb[4];
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) cb[jj] = *reinterpret_cast<const double2*>(src + (4 + jj) * 64);
+#pragma unroll
+            for (int ii = 0; ii < HI; ++ii) {
+                const double2 ca = *reinterpret_cast<const double2*>(src + ii * 64);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) dmma(acc[ii][jj][0], acc[ii][jj][1], ca.x, cb[jj].x);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) dmma(acc[ii][jj][0], acc[ii][jj][1], ca.y, cb[jj].y);
+            }
         }
-#pragma unroll
-        for (int ii = 0; ii < HI; ++ii)
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-                if (!DIAG || jj <= ii) dmma(acc[ii][jj][0], acc[ii][jj][1], ca[ii].x, cb[jj].x);
-#pragma unroll
-        for (int ii = 0; ii < HI; ++ii)
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-                if (!DIAG || jj <= ii) dmma(acc[ii][jj][0], acc[ii][jj][1], ca[ii].y, cb[jj].y);
         st_rd = (st_rd + 1 == ST) ? 0 : st_rd + 1;
-        st_wr = (st_wr + 1 == ST) ? 0 : st_wr + 1;
     }
     fcp_wait<0>();
 }
 
-struct FlowGeom {
-    int NT, NB, npad, n;
-    unsigned rhs_off;
-    __device__ __forceinline__ unsigned tile_off(int I, int K) const {  // doubles from the workspace base
-        return (I < NT) ? ((unsigned)I * (I + 1) / 2 + K) * 64u : rhs_off + (unsigned)K * 64u;
-    }
-};
-
-// ---------------------------------------------------------------------------------------------- task G(b, g)
-template <int HI, int ST, int MODE>
-__device__ __forceinline__ void flow_task_g(FlowCtl& S, const FlowGeom& G, const FlowEntry<MODE>& entry,
-                                            const double* __restrict__ y, double* __restrict__ tiles,
+// ---------------------------------------------------------------------------------------------- task U(b, g)
+// W slot of macro column b (written by P(b)): diagonal tiles (jj, jj) hold W_jj = L_jj^-1, the tiles (jj, m < jj)
+// hold -L_jj,m of the factored 32 x 32 diagonal block, all in operand order.
+template <int HI, int ST>
+__device__ __forceinline__ void flow_task_u(FlowCtl& S, const NllArgs& a, double* __restrict__ tiles,
                                             double* __restrict__ wring, const int b, const int g, const int lane, long long& fph_t) {
+    const FlowGeom G(a);
     const int r = lane >> 2, q = lane & 3;
-    const bool is_rhs = (g >= G.NB);
-    const int I0 = is_rhs ? G.NT : 4 * g;
+    constexpr bool is_rhs = (HI == 1);  // the right-hand-side row (g == NB) is the only one-row group
+    const int I0 = 4 * g;               // g == NB: row 4 NB
     const int nrow = is_rhs ? 1 : min(4, G.NT - I0);
     const int ncol = min(4, G.NT - 4 * b);
     double acc[HI][4][2];
@@ -214,79 +315,91 @@ __device__ __forceinline__ void flow_task_g(FlowCtl& S, const FlowGeom& G, const
     for (int ii = 0; ii < HI; ++ii)
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) acc[ii][jj][0] = acc[ii][jj][1] = 0.0;
-    unsigned aoff[HI], boff[4];
-#pragma unroll
-    for (int ii = 0; ii < HI; ++ii) aoff[ii] = G.tile_off(I0 + min(ii, nrow - 1), 0) + 2 * lane;
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj) boff[jj] = G.tile_off(4 * b + min(jj, ncol - 1), 0) + 2 * lane;
-    strip_update<HI, false, ST>(acc, tiles, aoff, boff, 4 * b, wring + 2 * lane);
+    strip_update<HI, false, ST>(acc, tiles + G.tile_off(I0, 0) + 2 * lane, tiles + G.tile_off(4 * b, 0) + 2 * lane, G.rowstride,
+                                4 * b, wring + 2 * lane, (a.l2mode & 1) != 0);
     FPH_MARK(8);
-
-    // correlation entries of the block -> scratch (accumulator positions: each lane re-reads its own elements)
-    double* const scr = wring;
-#pragma unroll 1
-    for (int e = 0; e < HI * 4; ++e) {
-        const int ii = e >> 2, jj = e & 3;
-        double v0 = 0.0, v1 = 0.0;
-        if (ii < nrow && jj < ncol) {
-            const int col = 8 * (4 * b + jj) + 2 * q;
-            if (!is_rhs) {
-                entry(8 * (I0 + ii) + r, col, v0, v1);
-            } else {  // rows: y^T, 1^T, zeros
-                if (r == 0) {
-                    if (col < G.n) v0 = __ldg(y + col);
-                    if (col + 1 < G.n) v1 = __ldg(y + col + 1);
-                } else if (r == 1) {
-                    v0 = (col < G.n) ? 1.0 : 0.0;
-                    v1 = (col + 1 < G.n) ? 1.0 : 0.0;
-                }
-            }
-        }
-        st_acc(scr + e * 64, lane, v0, v1);
-    }
+    if (!is_rhs) wait_ge(&S.erow[g], b + 1);  // the block's entries are parked in its tile slots (lane order)
     FPH_MARK(9);
-    // C = R - sum, in place
+    // C = R - sum -> scratch, accumulator positions
+    double* const scr = wring;
+    const double* const slots = tiles + 2 * lane;
 #pragma unroll
     for (int ii = 0; ii < HI; ++ii)
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
-            double v0, v1;
-            ld_acc(scr + (ii * 4 + jj) * 64, lane, v0, v1);
-            st_acc(scr + (ii * 4 + jj) * 64, lane, v0 - acc[ii][jj][0], v1 - acc[ii][jj][1]);
-            acc[ii][jj][0] = acc[ii][jj][1] = 0.0;
+            double v0 = 0.0, v1 = 0.0;
+            if (ii < nrow && jj < ncol) {
+                if (!is_rhs) {
+                    const double2 rv = __ldcg(reinterpret_cast<const double2*>(slots + G.tile_off(I0 + ii, 4 * b + jj)));
+                    v0 = rv.x - acc[ii][jj][0];
+                    v1 = rv.y - acc[ii][jj][1];
+                } else {  // rows: y^T, 1^T, zeros
+                    const int col = 8 * (4 * b + jj) + 2 * q;
+                    if (r == 0) {
+                        if (col < G.n) v0 = __ldg(a.y + col);
+                        if (col + 1 < G.n) v1 = __ldg(a.y + col + 1);
+                    } else if (r == 1) {
+                        v0 = (col < G.n) ? 1.0 : 0.0;
+                        v1 = (col + 1 < G.n) ? 1.0 : 0.0;
+                    }
+                    v0 -= acc[ii][jj][0];
+                    v1 -= acc[ii][jj][1];
+                }
+            }
+            st_acc(scr + (ii * 4 + jj) * 64, lane, v0, v1);
         }
-    __syncwarp();
-    // X = C W^T :  X[:, jj] = sum_{m <= jj} C[:, m] W[jj][m]^T
+    // the factor of the diagonal block is needed only now
+    wait_ge(&S.pdone, b + 1);
+    FPH_MARK(7);
+    if (*(volatile int*)&S.failed != 0) return;
+    // X = C L_bb^-T by block forward substitution over the 4 tile columns, in place in the scratch:
+    //   T_jj = C_jj + sum_{m<jj} X_m (-L_jj,m)^T ,  X_jj = T_jj W_jj^T     (slot (ii, jj): C -> T -> X)
     const double* Wb = S.W[b & 1];
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
-        double2 cf[HI];
+    for (int jj = 0; jj < 4; ++jj) {
+        double t[HI][2];
 #pragma unroll
-        for (int ii = 0; ii < HI; ++ii) cf[ii] = ld_frag(scr + (ii * 4 + m) * 64, lane);
+        for (int ii = 0; ii < HI; ++ii) ld_acc(scr + (ii * 4 + jj) * 64, lane, t[ii][0], t[ii][1]);
 #pragma unroll
-        for (int jj = m; jj < 4; ++jj) {
-            const double2 w = ld_frag(Wb + (jj * (jj + 1) / 2 + m) * 64, lane);
+        for (int m = 0; m < jj; ++m) {
+            const double2 nl = ld_frag(Wb + (jj * (jj + 1) / 2 + m) * 64, lane);
 #pragma unroll
-            for (int ii = 0; ii < HI; ++ii) dmma(acc[ii][jj][0], acc[ii][jj][1], cf[ii].x, w.x);
-#pragma unroll
-            for (int ii = 0; ii < HI; ++ii) dmma(acc[ii][jj][0], acc[ii][jj][1], cf[ii].y, w.y);
+            for (int ii = 0; ii < HI; ++ii) {
+                const double2 xf = ld_frag(scr + (ii * 4 + m) * 64, lane);
+                dmma(t[ii][0], t[ii][1], xf.x, nl.x);
+                dmma(t[ii][0], t[ii][1], xf.y, nl.y);
+            }
         }
+        if (jj > 0) {
+#pragma unroll
+            for (int ii = 0; ii < HI; ++ii) st_acc(scr + (ii * 4 + jj) * 64, lane, t[ii][0], t[ii][1]);
+        }
+        __syncwarp();
+        const double2 w = ld_frag(Wb + (jj * (jj + 1) / 2 + jj) * 64, lane);
+        double2 tf[HI];
+#pragma unroll
+        for (int ii = 0; ii < HI; ++ii) tf[ii] = ld_frag(scr + (ii * 4 + jj) * 64, lane);
+        __syncwarp();  // every lane has its T fragments: the slots may take X
+#pragma unroll
+        for (int ii = 0; ii < HI; ++ii) {
+            double x0 = 0.0, x1 = 0.0;
+            dmma(x0, x1, tf[ii].x, w.x);
+            dmma(x0, x1, tf[ii].y, w.y);
+            if (ii < nrow && jj < ncol) st_acc(tiles + G.tile_off(I0 + ii, 4 * b + jj), lane, x0, x1);
+            if (jj < 3) st_acc(scr + (ii * 4 + jj) * 64, lane, x0, x1);
+        }
+        __syncwarp();  // X_jj visible (after the last column: the scratch is free for the next task's copies)
     }
-#pragma unroll
-    for (int ii = 0; ii < HI; ++ii)
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj)
-            if (ii < nrow && jj < ncol) st_acc(tiles + G.tile_off(I0 + ii, 4 * b + jj), lane, acc[ii][jj][0], acc[ii][jj][1]);
-    __syncwarp();  // every lane is done with the scratch before the next task's copies land in it
     FPH_MARK(10);
 }
 
 // ---------------------------------------------------------------------------------------------- task P(b)
 // returns false when a pivot is not positive
-template <int ST, int MODE>
-__device__ __forceinline__ bool flow_task_p(FlowCtl& S, const FlowGeom& G, const FlowEntry<MODE>& entry,
-                                            const double* __restrict__ tiles, double* __restrict__ wring, const int b,
-                                            const int lane, double& logsum, long long& fph_t) {
+template <int ST>
+__device__ __forceinline__ bool flow_task_p(FlowCtl& S, const NllArgs& a, double* __restrict__ tiles,
+                                            double* __restrict__ wring, const int b, const int lane, double& logsum,
+                                            long long& fph_t) {
+    const FlowGeom G(a);
     const int r = lane >> 2, q = lane & 3;
     const int nrow = min(4, G.NT - 4 * b);
     double acc[4][4][2];
@@ -294,94 +407,93 @@ __device__ __forceinline__ bool flow_task_p(FlowCtl& S, const FlowGeom& G, const
     for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) acc[ii][jj][0] = acc[ii][jj][1] = 0.0;
-    unsigned aoff[4], boff[4];
-#pragma unroll
-    for (int ii = 0; ii < 4; ++ii) {
-        aoff[ii] = G.tile_off(4 * b + min(ii, nrow - 1), 0) + 2 * lane;
-        boff[ii] = aoff[ii];
-    }
-    strip_update<4, true, ST>(acc, tiles, aoff, boff, 4 * b, wring + 2 * lane);
+    strip_update<4, true, ST>(acc, tiles + G.tile_off(4 * b, 0) + 2 * lane, tiles, G.rowstride, 4 * b, wring + 2 * lane, false);
     FPH_MARK(2);
-
+    wait_ge(&S.erow[b], b + 1);  // E(b, b) has parked the diagonal block's entries
+    FPH_MARK(3);
     // D = R - sum as a plain 32 x 32 block, column-major: Sm[c * 32 + i]
     double* const Sm = wring;
-#pragma unroll 1
-    for (int e = 0; e < 10; ++e) {
-        const int ii = (e >= 6) ? 3 : (e >= 3) ? 2 : (e >= 1) ? 1 : 0;
-        const int jj = e - ii * (ii + 1) / 2;
-        double v0, v1;
-        if (ii < nrow) {
-            entry(8 * (4 * b + ii) + r, 8 * (4 * b + jj) + 2 * q, v0, v1);
-        } else {  // beyond the matrix: identity
-            v0 = (ii == jj && r == 2 * q) ? 1.0 : 0.0;
-            v1 = (ii == jj && r == 2 * q + 1) ? 1.0 : 0.0;
-        }
-        Sm[(8 * jj + 2 * q) * 32 + 8 * ii + r] = v0;
-        Sm[(8 * jj + 2 * q + 1) * 32 + 8 * ii + r] = v1;
-    }
+    double* const INV = S.inv;
+    const double* const slots = tiles + 2 * lane;
 #pragma unroll
     for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
-        for (int jj = 0; jj <= ii; ++jj)
+        for (int jj = 0; jj <= ii; ++jj) {
+            double v0, v1;
             if (ii < nrow) {
-                Sm[(8 * jj + 2 * q) * 32 + 8 * ii + r] -= acc[ii][jj][0];
-                Sm[(8 * jj + 2 * q + 1) * 32 + 8 * ii + r] -= acc[ii][jj][1];
+                const double2 rv = __ldcg(reinterpret_cast<const double2*>(slots + G.tile_off(4 * b + ii, 4 * b + jj)));
+                v0 = rv.x - acc[ii][jj][0];
+                v1 = rv.y - acc[ii][jj][1];
+            } else {  // beyond the matrix: identity
+                v0 = (ii == jj && r == 2 * q) ? 1.0 : 0.0;
+                v1 = (ii == jj && r == 2 * q + 1) ? 1.0 : 0.0;
             }
+            Sm[(8 * jj + 2 * q) * 32 + 8 * ii + r] = v0;
+            Sm[(8 * jj + 2 * q + 1) * 32 + 8 * ii + r] = v1;
+        }
     __syncwarp();
 
-    FPH_MARK(3);
-    // Cholesky, lane = row: column j of L = (D_ij - sum_{c<j} L_ic L_jc) / L_jj
+    // Cholesky, lane = row i: L_ij = (D_ij - sum_{c<j} L_ic L_jc) / L_jj.  The part of the sum that does not need
+    // column j-1 (c < j-1) is accumulated one step early, under the latency of the pivot's reciprocal square root.
     bool ok = true;
-    double prod = 1.0, myinv = 0.0;
+    double prod = 1.0, part = 0.0;
     logsum = 0.0;
 #pragma unroll 1
     for (int j = 0; j < 32; ++j) {
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        int c = 0;
-        for (; c + 4 <= j; c += 4) {
-            s0 = fma(Sm[c * 32 + lane], Sm[c * 32 + j], s0);
-            s1 = fma(Sm[(c + 1) * 32 + lane], Sm[(c + 1) * 32 + j], s1);
-            s2 = fma(Sm[(c + 2) * 32 + lane], Sm[(c + 2) * 32 + j], s2);
-            s3 = fma(Sm[(c + 3) * 32 + lane], Sm[(c + 3) * 32 + j], s3);
-        }
-        for (; c < j; ++c) s0 = fma(Sm[c * 32 + lane], Sm[c * 32 + j], s0);
-        const double aij = Sm[j * 32 + lane] - ((s0 + s1) + (s2 + s3));
+        double aij = Sm[j * 32 + lane] - part;
+        if (j > 0) aij = fma(-Sm[(j - 1) * 32 + lane], Sm[(j - 1) * 32 + j], aij);
         const double d = __shfl_sync(0xffffffffu, aij, j);
         ok = ok && (d > 1e-30);  // also false for NaN
         const double inv = rsqrt_pivot(d);
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        if (j < 31) {
+            const double* cj = Sm + j + 1;
+            int c = 0;
+            for (; c + 4 <= j; c += 4) {
+                s0 = fma(Sm[c * 32 + lane], cj[c * 32], s0);
+                s1 = fma(Sm[(c + 1) * 32 + lane], cj[(c + 1) * 32], s1);
+                s2 = fma(Sm[(c + 2) * 32 + lane], cj[(c + 2) * 32], s2);
+                s3 = fma(Sm[(c + 3) * 32 + lane], cj[(c + 3) * 32], s3);
+            }
+            for (; c < j; ++c) s0 = fma(Sm[c * 32 + lane], cj[c * 32], s0);
+        }
+        part = (s0 + s1) + (s2 + s3);
         prod *= d;
         if ((j & 7) == 7) {  // fold before the product of pivots can underflow
             logsum += log(prod);
             prod = 1.0;
         }
-        if (lane == j) myinv = inv;
+        if (lane == j) INV[j] = inv;
         if (lane >= j) Sm[j * 32 + lane] = aij * inv;  // own element of column j: no cross-lane hazard
         __syncwarp();
     }
     FPH_MARK(4);
     if (!ok) return false;
 
-    // W = L^-1, lane = column m: forward substitution; x_c(m) lives at its final place in the W slot
     if (b >= 2) wait_ge(&S.coldone[b - 2], G.NB - (b - 2));  // the slot's previous users are done
     FPH_MARK(5);
     double* const Wb = S.W[b & 1];
-    const int mb = lane >> 3, mm = lane & 7;
-    const int mpos = 2 * (mm & 3) + (mm >> 2);
-#pragma unroll 1
-    for (int i = 0; i < 32; ++i) {
-        const double inv_i = __shfl_sync(0xffffffffu, myinv, i);
-        if (i >= 8 * mb) {
-            double s0 = 0.0, s1 = 0.0;
-            int c = 8 * mb;
-            for (; c + 2 <= i; c += 2) {
-                s0 = fma(Sm[c * 32 + i], Wb[((c >> 3) * ((c >> 3) + 1) / 2 + mb) * 64 + 8 * (c & 7) + mpos], s0);
-                s1 = fma(Sm[(c + 1) * 32 + i],
-                         Wb[(((c + 1) >> 3) * (((c + 1) >> 3) + 1) / 2 + mb) * 64 + 8 * ((c + 1) & 7) + mpos], s1);
-            }
-            if (c < i) s0 = fma(Sm[c * 32 + i], Wb[((c >> 3) * ((c >> 3) + 1) / 2 + mb) * 64 + 8 * (c & 7) + mpos], s0);
-            const double xi = (((i == lane) ? 1.0 : 0.0) - (s0 + s1)) * inv_i;
-            Wb[((i >> 3) * ((i >> 3) + 1) / 2 + mb) * 64 + 8 * (i & 7) + mpos] = xi;
+    {   // W_tt = L_tt^-1 of the four 8 x 8 diagonal tiles: lane = (tile t, column m), forward substitution
+        const int t = lane >> 3, m = lane & 7;
+        double x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            double s = (i == m) ? 1.0 : 0.0;
+#pragma unroll
+            for (int c = 0; c < i; ++c) s = fma(-Sm[(8 * t + c) * 32 + 8 * t + i], x[c], s);
+            x[i] = s * INV[8 * t + i];
+            Wb[(t * (t + 1) / 2 + t) * 64 + tile_pos(i, m)] = x[i];
         }
+        // -L of the six off-diagonal tiles, operand order
+#pragma unroll
+        for (int jj = 1; jj < 4; ++jj)
+#pragma unroll
+            for (int mt = 0; mt < jj; ++mt) {
+                double2 v;
+                v.x = -Sm[(8 * mt + q) * 32 + 8 * jj + r];
+                v.y = -Sm[(8 * mt + q + 4) * 32 + 8 * jj + r];
+                *reinterpret_cast<double2*>(Wb + (jj * (jj + 1) / 2 + mt) * 64 + 2 * lane) = v;
+            }
     }
     __syncwarp();
     FPH_MARK(6);
@@ -389,30 +501,29 @@ __device__ __forceinline__ bool flow_task_p(FlowCtl& S, const FlowGeom& G, const
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
-template <int LW, int ST, int MODE>
-__global__ void __launch_bounds__(LW * 32, 16 / LW) krig_nll_flow_kernel(const NllArgs a) {
+// CPS = CTAs per SM the register allocation is sized for: 12 warps per SM -> 168 registers (at 128 registers ptxas
+// spills accumulators inside the k-loop)
+template <int LW, int ST, int MODE, int CPS>
+__global__ void __launch_bounds__(LW * 32, CPS) krig_nll_flow_kernel(const NllArgs a) {
     __shared__ FlowCtl S;
     extern __shared__ __align__(16) double dyn_s[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    FlowGeom G;
-    G.NT = a.npad / 8;
-    G.NB = (G.NT + 3) / 4;
-    G.npad = a.npad;
-    G.n = a.n;
-    G.rhs_off = (unsigned)G.NT * (G.NT + 1) / 2 * 64;
+    const FlowGeom G(a);
     const int NB = G.NB;
-    const size_t tile_doubles = chol_tiles(G.NT, 1) * 64;
-    double* const tiles = a.workspace + (size_t)blockIdx.x * tile_doubles;
+    double* const tiles = a.workspace + (size_t)blockIdx.x * flow_ws_doubles(G.NT);
     double* const wring = dyn_s + (size_t)wid * (ST * 8 * 64);
     for (int j = threadIdx.x; j < E2TAB; j += blockDim.x) S.etab[j] = g_e2tab[j];
-    const int total_tasks = 2 + (NB - 1) * (NB + 1) - (NB - 2) * (NB - 1) / 2;
-    FlowEntry<MODE> entry{&S, MODE == 0 ? a.dtab : a.log2tab, a.k, a.npad, false};
+    const int total_tasks = NB * NB + 2 * NB;
+    const size_t ntri = (size_t)G.NT * (G.NT + 1) / 2;
 
-    for (long long c = blockIdx.x; c < a.C; c += gridDim.x) {
+    for (int iter = 0;; ++iter) {
+        const long long c = (long long)blockIdx.x + (long long)iter * gridDim.x;
+        if (c >= a.C) break;
         __syncthreads();  // the previous candidate's epilogue is done
         for (int j = threadIdx.x; j <= NB; j += blockDim.x) {
             S.rowdone[j] = 0;
             S.coldone[j] = 0;
+            S.erow[j] = 0;
         }
         if (threadIdx.x == 0) {
             S.pdone = 0;
@@ -420,8 +531,9 @@ __global__ void __launch_bounds__(LW * 32, 16 / LW) krig_nll_flow_kernel(const N
             S.failed = 0;
             S.logacc = 0.0;
         }
-        if (threadIdx.x < a.k) {
-            const int d = threadIdx.x;
+        if (threadIdx.x < KMAX) {
+            const int d = min((int)threadIdx.x, a.k - 1);
+            const bool real = (int)threadIdx.x < a.k;
             const double LOG2E = 1.4426950408889634;
             if (MODE == 0) {
                 long long tk = 1;
@@ -432,76 +544,92 @@ __global__ void __launch_bounds__(LW * 32, 16 / LW) krig_nll_flow_kernel(const N
                     it /= a.T;
                     ip /= a.P;
                 }
-                S.th2[d] = a.theta_axis[it % a.T] * LOG2E;
-                S.pw[d] = 1.0;
-                S.off[d] = ((long long)d * a.P + (ip % a.P)) * (long long)a.npad * a.npad;
+                S.th2[threadIdx.x] = real ? a.theta_axis[it % a.T] * LOG2E : 0.0;
+                S.pw[threadIdx.x] = 1.0;
+                S.off[threadIdx.x] = ((long long)d * a.P + (ip % a.P)) * (long long)ntri * 64;
             } else {
-                S.th2[d] = a.theta[c * a.k + d] * LOG2E;
-                S.pw[d] = a.p[c * a.k + d];
-                S.off[d] = (long long)d * a.npad * a.npad;
+                S.th2[threadIdx.x] = real ? a.theta[c * a.k + d] * LOG2E : 0.0;
+                S.pw[threadIdx.x] = real ? a.p[c * a.k + d] : 1.0;
+                S.off[threadIdx.x] = 64ll * d;
             }
         }
         __syncthreads();
-        if (MODE == 1) {
+        if (threadIdx.x == 0) {
             bool sp = true;
             for (int d = 0; d < a.k; ++d) sp = sp && (S.pw[d] >= 0.25) && (S.pw[d] <= 2.3);
-            entry.safe_p = sp;
+            S.safe_p = sp ? 1 : 0;
         }
+        __syncthreads();
 
         long long fph_t = clock64();
         (void)fph_t;
-        int cb = 0, cbase = 0;  // macro column of the last decoded task and the queue position of its first task
         while (true) {
             int t = 0;
             if (lane == 0) t = atomicAdd(&S.next_task, 1);
             t = __shfl_sync(0xffffffffu, t, 0);
             if (t >= total_tasks) break;
-            bool is_p;
-            int b, g = 0;
-            if (t == 0) {
-                is_p = true;
+            // decode the queue position: kind 0 = E, 1 = P, 2 = U
+            int kind, b, g;
+            if (t <= NB) {  // prologue: E(0,0) P(0) E(0,1..NB-1)
+                kind = (t == 1) ? 1 : 0;
                 b = 0;
+                g = (t <= 1) ? 0 : t - 1;
             } else {
-                const int u = t - 1;
+                int l = t - (NB + 1), cb = 0;
                 while (true) {
-                    const int cnt = (cb < NB - 1) ? NB - cb + 1 : 1;
-                    if (u < cbase + cnt) break;
-                    cbase += cnt;
+                    const int m = NB - cb - 1;
+                    const int cnt = (m >= 1) ? 2 * m + 2 : 1;
+                    if (l < cnt) break;
+                    l -= cnt;
                     ++cb;
                 }
-                const int local = u - cbase;
-                if (cb < NB - 1 && local == 1) {
-                    is_p = true;
-                    b = cb + 1;
+                const int m = NB - cb - 1;
+                if (m < 1 || l == 2 * m + 1) {
+                    kind = 2, b = cb, g = NB;
+                } else if (l == 0) {
+                    kind = 0, b = cb + 1, g = cb + 1;
+                } else if (l == 1) {
+                    kind = 2, b = cb, g = cb + 1;
+                } else if (l == 2) {
+                    kind = 1, b = cb + 1, g = cb + 1;
                 } else {
-                    is_p = false;
-                    b = cb;
-                    g = (cb < NB - 1) ? (local == 0 ? cb + 1 : cb + local) : NB;
+                    const int j = 2 + ((l - 3) >> 1);
+                    if (((l - 3) & 1) == 0) kind = 2, b = cb, g = cb + j;
+                    else kind = 0, b = cb + 1, g = cb + j;
                 }
             }
             FPH_MARK(0);
-            if (is_p) {
+            const bool failed = *(volatile int*)&S.failed != 0;
+            if (kind == 0) {
+                if (!failed) flow_task_e<MODE>(S, a, tiles, b, g, lane);
+                FPH_MARK(12);
+                __threadfence_block();
+                __syncwarp();
+                wait_ge(&S.erow[g], b);  // keep the per-row counter monotonic
+                if (lane == 0) *(volatile int*)&S.erow[g] = b + 1;
+                FPH_MARK(13);
+            } else if (kind == 1) {
                 if (b > 0) wait_ge(&S.rowdone[b], b);
                 FPH_MARK(1);
-                const bool failed = *(volatile int*)&S.failed != 0;
+                const bool failed2 = *(volatile int*)&S.failed != 0;
                 bool ok = true;
                 double logsum = 0.0;
-                if (!failed) ok = flow_task_p<ST, MODE>(S, G, entry, tiles, wring, b, lane, logsum, fph_t);
+                if (!failed2) ok = flow_task_p<ST>(S, a, tiles, wring, b, lane, logsum, fph_t);
                 __syncwarp();
                 if (lane == 0) {
-                    if (!failed && ok) S.logacc += logsum;
+                    if (!failed2 && ok) S.logacc += logsum;
                     if (!ok) *(volatile int*)&S.failed = 1;
                     __threadfence_block();
                     *(volatile int*)&S.pdone = b + 1;
                 }
             } else {
-                wait_ge(&S.pdone, b + 1);
+                wait_ge(&S.rowdone[b], b);  // the B strip; P(b) itself is awaited right before the solve
                 wait_ge(&S.rowdone[g], b);
                 FPH_MARK(7);
-                const bool failed = *(volatile int*)&S.failed != 0;
-                if (!failed) {
-                    if (g < NB) flow_task_g<4, ST, MODE>(S, G, entry, a.y, tiles, wring, b, g, lane, fph_t);
-                    else flow_task_g<1, ST, MODE>(S, G, entry, a.y, tiles, wring, b, g, lane, fph_t);
+                const bool failed2 = *(volatile int*)&S.failed != 0;
+                if (!failed2) {
+                    if (g < NB) flow_task_u<4, ST>(S, a, tiles, wring, b, g, lane, fph_t);
+                    else flow_task_u<1, ST>(S, a, tiles, wring, b, g, lane, fph_t);
                 }
                 __threadfence_block();
                 __syncwarp();
@@ -515,32 +643,73 @@ __global__ void __launch_bounds__(LW * 32, 16 / LW) krig_nll_flow_kernel(const N
         FPH_MARK(11);
         if (wid == 0) {
             double nll = INFINITY;
-            if (S.failed == 0) nll = nll_epilogue(tiles + G.rhs_off, a.n, lane, 0.5 * S.logacc, nullptr, nullptr);
-            if (lane == 0) a.nll_out[c] = nll;
+            if (S.failed == 0)
+                nll = nll_epilogue(tiles + G.tile_off(4 * NB, 0), a.n, lane, 0.5 * S.logacc, nullptr, nullptr);
+            if (lane == 0) a.nll_out[(long long)blockIdx.x + (long long)iter * gridDim.x] = nll;
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-__global__ void log2tab_kernel(const double* __restrict__ X, int n, int k, int npad, double* __restrict__ LG) {
-    const size_t per = (size_t)npad * npad;
-    const size_t total = per * k;
+// element t of a tile-packed table -> (tri, slot e) -> matrix indices (i, j) of that slot
+__device__ __forceinline__ void packed_ij(size_t tri, int e, int& i, int& j) {
+    int I = (int)((sqrt(8.0 * (double)tri + 1.0) - 1.0) * 0.5);
+    while ((size_t)I * (I + 1) / 2 > tri) --I;
+    while ((size_t)(I + 1) * (I + 2) / 2 <= tri) ++I;
+    const int J = (int)(tri - (size_t)I * (I + 1) / 2);
+    const int lane = e >> 1;
+    i = 8 * I + (lane >> 2);
+    j = 8 * J + 2 * (lane & 3) + (e & 1);
+}
+// list mode: LG[(tri * k + d) * 64 + e] = 512 log2|dx_d|, clamped: |dx| = 0 -> 2^(-430 p) ~ 0, padding (identity)
+// -> off-diagonal 2^(430 p) ~ inf, diagonal ~ 0
+__global__ void log2tab_packed_kernel(const double* __restrict__ X, int n, int k, size_t ntri, double* __restrict__ LG) {
+    const size_t total = ntri * k * 64;
     for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-        const int j = (int)(t % npad);
-        const int i = (int)((t / npad) % npad);
-        const int d = (int)(t / per);
-        // 512 log2|dx|, clamped: |dx| = 0 -> 2^(-430 p) ~ 0, padding (identity) -> 2^(430 p) ~ inf
+        const int e = (int)(t & 63);
+        const int d = (int)((t >> 6) % k);
+        int i, j;
+        packed_ij((t >> 6) / k, e, i, j);
         double v = (i == j) ? -E2_CLAMP : E2_CLAMP;
         if (i < n && j < n)
             v = fmin(fmax(512.0 * log2(fabs(X[(size_t)i * k + d] - X[(size_t)j * k + d])), -E2_CLAMP), E2_CLAMP);
         LG[t] = v;
     }
 }
+// grid mode: D[((d * P + q) * ntri + tri) * 64 + e] = |dx_d|^p_axis[q]; padding: identity (see dtab_kernel)
+__global__ void dtab_packed_kernel(const double* __restrict__ X, int n, int k, size_t ntri, const double* __restrict__ p_axis,
+                                   int P, double* __restrict__ D) {
+    const size_t total = ntri * 64 * k * P;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int e = (int)(t & 63);
+        const size_t tri = (t >> 6) % ntri;
+        const int dq = (int)((t >> 6) / ntri);
+        const int q = dq % P, d = dq / P;
+        int i, j;
+        packed_ij(tri, e, i, j);
+        double v = (i == j) ? 0.0 : 1.7976931348623157e308;
+        if (i < n && j < n) v = pow(fabs(X[(size_t)i * k + d] - X[(size_t)j * k + d]), p_axis[q]);
+        D[t] = v;
+    }
+}
+size_t flow_table_doubles(int n) {
+    const size_t NT = (size_t)(n + 7) / 8;
+    return NT * (NT + 1) / 2 * 64;
+}
 cudaError_t launch_log2tab(const double* X, int n, int k, int npad, double* LG, cudaStream_t st) {
-    const size_t total = (size_t)npad * npad * k;
+    const size_t ntri = (size_t)(npad / 8) * (npad / 8 + 1) / 2;
+    const size_t total = ntri * 64 * k;
     int grid = (int)((total + 255) / 256);
     if (grid > 148 * 16) grid = 148 * 16;
-    log2tab_kernel<<<grid, 256, 0, st>>>(X, n, k, npad, LG);
+    log2tab_packed_kernel<<<grid, 256, 0, st>>>(X, n, k, ntri, LG);
+    return cudaGetLastError();
+}
+cudaError_t launch_dtab_packed(const double* X, int n, int k, int npad, const double* p_axis, int P, double* D, cudaStream_t st) {
+    const size_t ntri = (size_t)(npad / 8) * (npad / 8 + 1) / 2;
+    const size_t total = ntri * 64 * k * P;
+    int grid = (int)((total + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    dtab_packed_kernel<<<grid, 256, 0, st>>>(X, n, k, ntri, p_axis, P, D);
     return cudaGetLastError();
 }
 
@@ -557,12 +726,12 @@ static cudaError_t upload_e2tab() {
     return e;
 }
 
-template <int LW, int ST>
+template <int LW, int ST, int CPS>
 static cudaError_t launch_flow_t(NllArgs a, int mode, cudaStream_t st) {
     const int NT = a.npad / 8;
-    const size_t tile_bytes = chol_tiles(NT, 1) * 512;
+    const size_t tile_bytes = flow_ws_doubles(NT) * 8;
     const size_t smem = (size_t)LW * ST * 8 * 512;
-    auto kern = (mode == 0) ? krig_nll_flow_kernel<LW, ST, 0> : krig_nll_flow_kernel<LW, ST, 1>;
+    auto kern = (mode == 0) ? krig_nll_flow_kernel<LW, ST, 0, CPS> : krig_nll_flow_kernel<LW, ST, 1, CPS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -603,13 +772,17 @@ cudaError_t launch_nll_flow(NllArgs a, int mode, cudaStream_t st) {
     cudaError_t e = upload_e2tab();
     if (e != cudaSuccess) return e;
     static const int cfg = [] { const char* v = getenv("SMB_FLOW_CFG"); return v ? atoi(v) : 0; }();
+    static const int l2 = [] { const char* v = getenv("SMB_FLOW_L2"); return v ? atoi(v) : 1; }();
+    a.l2mode = l2;
     const int NT = a.npad / 8;
-    int sel = cfg ? cfg : (NT <= 48 ? 42 : 83);
+    int sel = cfg ? cfg : (NT <= 48 ? 43 : 63);
     switch (sel) {
-        case 42: return launch_flow_t<4, 2>(a, mode, st);
-        case 43: return launch_flow_t<4, 3>(a, mode, st);
-        case 82: return launch_flow_t<8, 2>(a, mode, st);
-        default: return launch_flow_t<8, 3>(a, mode, st);
+        case 42: return launch_flow_t<4, 2, 4>(a, mode, st);
+        case 43: return launch_flow_t<4, 3, 3>(a, mode, st);   // 12 warps / SM, 168 registers
+        case 63: return launch_flow_t<6, 3, 2>(a, mode, st);   // 12 warps / SM, 168 registers
+        case 64: return launch_flow_t<6, 4, 2>(a, mode, st);
+        case 82: return launch_flow_t<8, 2, 2>(a, mode, st);
+        default: return launch_flow_t<8, 3, 2>(a, mode, st);
     }
 }
 

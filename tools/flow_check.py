@@ -105,8 +105,9 @@ def main():
     if quick:
         timing = [(256, 8, 2368), (512, 8, 1184), (1024, 8, 592)]
     configs = [('flow default', {}, True), ('v1 macro-panel', {'SMB_LARGE_V1': '1'}, True)]
-    for cfg in ('42', '43', '82', '83'):
+    for cfg in ('42', '43', '63', '82', '83'):
         configs.append((f'flow cfg {cfg}', {'SMB_FLOW_CFG': cfg}, False))
+
     for name, env, with_parity in configs:
         spec = {'timing': timing}
         if with_parity:

@@ -26,9 +26,9 @@ L.smb_flow_phase_read(buf.ctypes.data, 1)
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record(); f(); b.record(); torch.cuda.synchronize()
 L.smb_flow_phase_read(buf.ctypes.data, 1)
-names = ['grab/decode', 'P wait rowdone', 'P k-loop', 'P entries', 'P cholesky', 'P wait W slot', 'P inverse', 'G wait', 'G k-loop',
-         'G entries', 'G solve+store', 'end barrier']
-tot = float(buf[:12].sum())
+names = ['grab/decode', 'P wait rowdone', 'P k-loop', 'P wait E', 'P load+cholesky', 'P wait W slot', 'P inverse', 'U wait (rows | P)', 'U k-loop',
+         'U wait E', 'U rmw+solve+store', 'end barrier', 'E compute', 'E signal']
+tot = float(buf[:14].sum())
 print(f'n={n} k={k} C={C} cfg={os.environ.get("SMB_FLOW_CFG", "default")}: {a.elapsed_time(b):.2f} ms; block 0 warp-cycles by phase (all warps summed): total {tot/1e6:.2f} M')
 for i, nm in enumerate(names):
     print(f'  {nm:16s} {buf[i]/1e3:12.1f} k  {100*buf[i]/tot:5.1f} %')
