@@ -240,7 +240,8 @@ __device__ __forceinline__ void flow_task_e(const FlowCtl& S, const NllArgs& a, 
 template <int HI, bool DIAG, int ST>
 __device__ __forceinline__ void strip_update(double (&acc)[HI][4][2], const double* __restrict__ abase,
                                              const double* __restrict__ bbase, const unsigned rowstride, const int nk,
-                                             double* __restrict__ ring /* + 2 * lane */, const bool stream_a) {
+                                             double* __restrict__ ring /* + 2 * lane */, const bool stream_a,
+                                             const int pf_lane, const int pfd) {
     auto issue = [&](int K, int stage) {
         // A strips are read once per macro column: evict_first keeps them from flushing the B strips and the tables
         // out of L2 (the policy is re-created here instead of living in two registers across the loop)
@@ -258,10 +259,21 @@ __device__ __forceinline__ void strip_update(double (&acc)[HI][4][2], const doub
         if (s < nk) issue(s, s);
         fcp_commit();
     }
+    // L2 prefetch PFD k-steps ahead of the ring: ONE instruction per k-step covers the 8 operand tiles of a step
+    // (lane l -> 128-byte line l % 4 of tile l / 4).  With only ST - 1 steps in flight per warp the k-loop ran at
+    // the L2-miss latency (a step of 32 DMMAs is 512 pipe cycles, a miss under load ~2000).
+    const int pl = pf_lane;  // lane index
+    const double* pf = ((pl < 16) ? abase - 2 * pl + (size_t)((pl >> 2) * rowstride)
+                                  : bbase - 2 * pl + (size_t)(((pl - 16) >> 2) * rowstride)) + (pl & 3) * 16;
+    const bool pf_on = pfd > 0 && ((pl < 16) ? (pl >> 2) < HI : !DIAG);
+    if (pf_on) {
+        for (int K = ST - 1; K < min(nk, pfd); ++K) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(pf + (size_t)K * 64));
+    }
     int st_rd = 0;
 #pragma unroll 1
     for (int K = 0; K < nk; ++K) {
         const int st_wr = (st_rd == 0) ? ST - 1 : st_rd - 1;
+        if (pf_on && K + pfd < nk) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(pf + (size_t)(K + pfd) * 64));
         if (K + ST - 1 < nk) issue(K + ST - 1, st_wr);
         fcp_commit();
         fcp_wait<ST - 1>();  // the copies of step K have landed
@@ -316,7 +328,7 @@ __device__ __forceinline__ void flow_task_u(FlowCtl& S, const NllArgs& a, double
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) acc[ii][jj][0] = acc[ii][jj][1] = 0.0;
     strip_update<HI, false, ST>(acc, tiles + G.tile_off(I0, 0) + 2 * lane, tiles + G.tile_off(4 * b, 0) + 2 * lane, G.rowstride,
-                                4 * b, wring + 2 * lane, (a.l2mode & 1) != 0);
+                                4 * b, wring + 2 * lane, (a.l2mode & 1) != 0, lane, a.l2mode >> 4);
     FPH_MARK(8);
     if (!is_rhs) wait_ge(&S.erow[g], b + 1);  // the block's entries are parked in its tile slots (lane order)
     FPH_MARK(9);
@@ -407,7 +419,8 @@ __device__ __forceinline__ bool flow_task_p(FlowCtl& S, const NllArgs& a, double
     for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) acc[ii][jj][0] = acc[ii][jj][1] = 0.0;
-    strip_update<4, true, ST>(acc, tiles + G.tile_off(4 * b, 0) + 2 * lane, tiles, G.rowstride, 4 * b, wring + 2 * lane, false);
+    strip_update<4, true, ST>(acc, tiles + G.tile_off(4 * b, 0) + 2 * lane, tiles, G.rowstride, 4 * b, wring + 2 * lane, false, lane,
+                              a.l2mode >> 4);
     FPH_MARK(2);
     wait_ge(&S.erow[b], b + 1);  // E(b, b) has parked the diagonal block's entries
     FPH_MARK(3);
@@ -753,7 +766,7 @@ static cudaError_t launch_flow_t(NllArgs a, int mode, cudaStream_t st) {
     return e != cudaSuccess ? e : e2;
 }
 
-// SMB_LARGE_V1=1 keeps n > 128 on the barrier-synchronised macro-panel kernel (krig_nll_large.cu; cross-check
+// SMB_LARGE_V1=1 keeps every n > 128 on the barrier-synchronised macro-panel kernel (krig_nll_large.cu; cross-check
 // in the tests); SMB_FLOW_CFG=<LW><ST> (e.g. 43, 82) overrides the warps-per-CTA / ring-depth choice (tuning).
 bool nll_uses_flow(int n) {
     static const bool v1 = [] {
@@ -762,7 +775,8 @@ bool nll_uses_flow(int n) {
         return (v && v[0] == '1') || (g && g[0] == '1');
     }();
     const int NT = (n + 7) / 8;
-    return !v1 && NT > 16 && (NT + 3) / 4 + 2 <= FLOW_MAXG;
+    // measured crossover against the macro-panel kernel (tools/flow_check.py): n = 320: 6.9 vs 7.0, n = 384: 8.0 vs 7.9
+    return !v1 && NT > 44 && (NT + 3) / 4 + 2 <= FLOW_MAXG;
 }
 
 cudaError_t launch_nll_flow(NllArgs a, int mode, cudaStream_t st) {
@@ -772,10 +786,11 @@ cudaError_t launch_nll_flow(NllArgs a, int mode, cudaStream_t st) {
     cudaError_t e = upload_e2tab();
     if (e != cudaSuccess) return e;
     static const int cfg = [] { const char* v = getenv("SMB_FLOW_CFG"); return v ? atoi(v) : 0; }();
-    static const int l2 = [] { const char* v = getenv("SMB_FLOW_L2"); return v ? atoi(v) : 1; }();
+    // bit 0: evict_first on the A strips; bits 4..: L2 prefetch distance in k-steps (0 = off)
+    static const int l2 = [] { const char* v = getenv("SMB_FLOW_L2"); return v ? atoi(v) : 1 + 16 * 8; }();
     a.l2mode = l2;
     const int NT = a.npad / 8;
-    int sel = cfg ? cfg : (NT <= 48 ? 43 : 63);
+    int sel = cfg ? cfg : (NT < 96 ? 42 : 63);  // 4 warps x 4 CTAs below n = 768, 6 warps x 2 CTAs (168 registers) above
     switch (sel) {
         case 42: return launch_flow_t<4, 2, 4>(a, mode, st);
         case 43: return launch_flow_t<4, 3, 3>(a, mode, st);   // 12 warps / SM, 168 registers

@@ -496,7 +496,7 @@ print(json.dumps(dict(a=[None if not np.isfinite(v) else float(v) for v in a], b
 
 
 def test_large_n_and_large_k(K):
-    """n = 2048 (macro-panel kernel, 17 MB of tiles per candidate) and k = 16 (SM_KMAX) against the oracle"""
+    """n = 2048 (dataflow kernel, 34 MB workspace per candidate) and k = 16 (SM_KMAX) against the oracle"""
     rng = np.random.default_rng(2048)
     X = rng.uniform(0, 1, (2048, 3))
     y = np.sin(3 * X.sum(axis=1)) + X[:, 0] ** 2
@@ -515,6 +515,94 @@ def test_large_n_and_large_k(K):
     ref16 = np.array([orc.nll_chol(X16, y16, 10. ** e16[c], p16[c]) for c in range(6)])
     cond16 = np.array([orc.cond2(orc.corr_matrix(X16, 10. ** e16[c], p16[c])) for c in range(6)])
     assert check_values(nll16, ref16, cond16, cond_max=1e12) == 6
+
+
+@pytest.mark.parametrize('n,k_', [(353, 2), (361, 5), (377, 16), (500, 3), (520, 1)])
+def test_dataflow_kernel_ragged_sizes(K, n, k_):
+    """n > 352 runs on the dataflow kernel (krig_nll_flow.cu): tile counts NT = 45, 46, 48, 63, 65 cover every
+    remainder of the 4-tile row groups / macro columns, k = 1 .. 16 every chunking of the entry evaluation"""
+    rng = np.random.default_rng(n * 100 + k_)
+    X = rng.uniform(0, 10, (n, k_))
+    y = np.sin(X.sum(axis=1)) + 0.1 * X[:, 0] ** 2
+    e = rng.uniform(-1.5, 0.3, (10, k_))
+    p = rng.uniform(1, 2, (10, k_))
+    p[0], p[1] = 2.0, 1.0
+    e[2] = -9.0                      # R ~ all ones: not numerically SPD -> +inf, the other candidates unaffected
+    p[3, 0] = 0.1                    # outside the guard-free range of the table-driven power (slow path)
+    p[4, -1] = 0.2
+    k = K(X, y)
+    nll = k.likelihood_batch(e, p)
+    ref = np.array([orc.nll_chol(X, y, 10. ** e[c], p[c]) for c in range(10)])
+    cond = np.array([orc.cond2(orc.corr_matrix(X, 10. ** e[c], p[c])) for c in range(10)])
+    if not np.isfinite(ref[2]):
+        assert nll[2] == np.inf
+    m = np.arange(10) != 2
+    assert check_values(nll[m], ref[m], cond[m], cond_max=1e11) >= 5
+    assert np.array_equal(nll, k.likelihood_batch(e, p))            # deterministic despite dynamic task order
+
+
+def test_dataflow_kernel_grid_mode_and_shards(K):
+    """grid mode at n = 400 (tile-packed |dx|^p tables), first-minimum index, and a sharded evaluation that is
+    bit-identical to the full one"""
+    rng = np.random.default_rng(400)
+    X = rng.uniform(0, 10, (400, 2))
+    y = np.sin(X.sum(axis=1)) + 0.1 * X[:, 0] ** 2
+    k = K(X, y)
+    T, P = 4, 3
+    th_axis = np.linspace(-1.5, 0.5, T)
+    p_axis = np.linspace(1., 2., P)
+    L = _cabi.lib()
+    from sm_b200 import device
+    d = k._dev()
+    dta, dpa = device.to_dev(10. ** th_axis), device.to_dev(p_axis)
+    C = T * T * P * P
+    out = device.empty(C)
+    bv, bi = device.empty(1), device.empty(1, dtype=torch.int64)
+    _cabi.check(L.sm_krig_nll_grid(device.ptr(d['X']), device.ptr(d['y']), 400, 2, device.ptr(dta), T, device.ptr(dpa), P, 0, C,
+                                   device.ptr(out), device.ptr(bv), device.ptr(bi), device.stream()))
+    torch.cuda.synchronize()
+    nll = out.cpu().numpy()
+    ref = np.empty(C)
+    cond = np.empty(C)
+    for c in range(C):
+        it, ip = c % (T * T), c // (T * T)
+        th = np.array([10. ** th_axis[(it // T ** dd) % T] for dd in range(2)])
+        pp = np.array([p_axis[(ip // P ** dd) % P] for dd in range(2)])
+        ref[c] = orc.nll_chol(X, y, th, pp)
+        cond[c] = orc.cond2(orc.corr_matrix(X, th, pp))
+    assert check_values(nll, ref, cond, cond_max=1e10) >= C // 2
+    assert int(bi.item()) == orc.first_min_vec(np.where(np.isfinite(nll), nll, np.inf))
+    half = device.empty(C - 50)
+    _cabi.check(L.sm_krig_nll_grid(device.ptr(d['X']), device.ptr(d['y']), 400, 2, device.ptr(dta), T, device.ptr(dpa), P, 50, C - 50,
+                                   device.ptr(half), None, None, device.stream()))
+    torch.cuda.synchronize()
+    assert np.array_equal(half.cpu().numpy(), nll[50:], equal_nan=True)
+
+
+def test_dataflow_vs_macro_panel_kernel(K):
+    """SMB_LARGE_V1=1 keeps n > 128 on the barrier-synchronised macro-panel kernel: both must agree"""
+    import json
+    import subprocess
+    import sys
+    script = r'''
+import json, os, sys
+import numpy as np
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), 'surrogate-models_b200'))
+from mylibs.kriging import Kriging
+from sm_b200 import workloads
+X3, y3 = workloads.c3_lhs1024(n=600, k=8)
+e, p = workloads.c3_candidates(40, 8)
+b = Kriging(X3, y3).likelihood_batch(e, p)
+print(json.dumps(dict(b=[float(v) for v in b])))
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    for flag in ('0', '1'):
+        env = dict(os.environ, SMB_LARGE_V1=flag)
+        r = subprocess.run([sys.executable, '-c', script], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[flag] = json.loads(r.stdout.strip().split('\n')[-1])
+    assert np.max(rel(np.array(out['0']['b']), np.array(out['1']['b']))) < 1e-10   # cond ~1e4
 
 
 def test_optimize_grid_end_to_end_r3(gold, K, capsys):
