@@ -333,20 +333,27 @@ def run_gpu(args):
                  'hbm_gbs_achieved': m * m * 32 / (pred_ms * 1e-3) / 1e9,
                  'mean_only_predictions_per_s': world * m * m / (pred_mean_ms * 1e-3)}
     del xq
-    # C3: 8-D Kriging, n = 1024 LHS samples, explicit candidate list (592 candidates per GPU here)
-    X3, y3 = workloads.c3_lhs1024()
-    e3, p3 = workloads.c3_candidates(592 * world, 8)
-    k3 = Kriging(X3, y3)
-    d3 = k3._dev()
-    th3 = device.to_dev(np.power(10., e3[rank * 592:(rank + 1) * 592]))
-    pp3 = device.to_dev(p3[rank * 592:(rank + 1) * 592])
-    out3 = device.empty(592)
-    c3_ms = timed_ms(lambda: _cabi.check(L.sm_krig_nll_batch(device.ptr(d3['X']), device.ptr(d3['y']), 1024, 8, device.ptr(th3),
-                                                               device.ptr(pp3), 592, 0, device.ptr(out3), None, None, stream)))
-    secondary_c3 = {'metric': 'kriging likelihood evaluations/s (n=1024, k=8, list mode)', 'value': world * 592 / (c3_ms * 1e-3),
-                    'unit': 'evals/s', 'candidates_per_gpu': 592, 'ms': c3_ms,
-                    'tflops_fma_only': flops_like(1024, 8) * 592 / (c3_ms * 1e-3) / 1e12,
-                    'frac_of_fp64_peak': flops_like(1024, 8) * 592 / (c3_ms * 1e-3) / 1e12 / peak_tf}
+    # C3 shape: 8-D Kriging on LHS samples, explicit candidate list (list mode), n = 1024 plus two neighbours of the
+    # large-n kernel range.  fractions: FMA-only (n^3/3 + (k+2) n^2 flop at the measured fp64 peak) and the
+    # two-resource bound of SURVEY.md 8(d) with (k+1) n(n-1)/2 exponentials at the measured exp() rate.
+    def large_n_point(n3, C3):
+        X3, y3 = workloads.c3_lhs1024(n=n3)
+        e3, p3 = workloads.c3_candidates(C3 * world, 8)
+        k3 = Kriging(X3, y3)
+        d3 = k3._dev()
+        th3 = device.to_dev(np.power(10., e3[rank * C3:(rank + 1) * C3]))
+        pp3 = device.to_dev(p3[rank * C3:(rank + 1) * C3])
+        out3 = device.empty(C3)
+        ms3 = timed_ms(lambda: _cabi.check(L.sm_krig_nll_batch(device.ptr(d3['X']), device.ptr(d3['y']), n3, 8, device.ptr(th3),
+                                                                 device.ptr(pp3), C3, 0, device.ptr(out3), None, None, stream)))
+        tf = flops_like(n3, 8) * C3 / (ms3 * 1e-3) / 1e12
+        t_bound3 = C3 * (flops_like(n3, 8) / (peak_tf * 1e12) + 9 * n3 * (n3 - 1) / 2 / (exp_gops * 1e9))
+        return {'n': n3, 'k': 8, 'value': world * C3 / (ms3 * 1e-3), 'unit': 'evals/s', 'candidates_per_gpu': C3, 'ms': ms3,
+                'tflops_fma_only': tf, 'frac_of_fp64_peak': tf / peak_tf, 'frac_two_resource': t_bound3 / (ms3 * 1e-3)}
+    c3pt = large_n_point(1024, 1184)
+    secondary_c3 = dict(c3pt, metric='kriging likelihood evaluations/s (n=1024, k=8, list mode)',
+                        kernel='krig_nll_flow_kernel<6,3,1,2> (n > 352: dataflow kernel; 128 < n <= 352: krig_nll_large_kernel)',
+                        other_sizes=[large_n_point(512, 2368), large_n_point(2048, 296)])
     # C4: gaussian RBF, n = 4096: weight solve + evaluation at 2e6 points per GPU
     from mylibs.rbf import RBF
     X4, y4 = workloads.c4_rbf4096()

@@ -22,7 +22,9 @@
 //           needs: rowdone[b] >= b, rowdone[g] >= b to start; erow[g] >= b+1 after the k-loop; pdone >= b+1 before
 //           the solve -- so the factorisation of the diagonal block runs in parallel with the updates (look-ahead).
 // Queue:  E(0,0) P(0) E(0,1..NB-1);  then per macro column b:
-//         E(b+1,b+1) U(b,b+1) P(b+1) [U(b,b+j) E(b+1,b+j)]_{j=2..} U(b,NB)
+//         E(b+1,b+1) U(b,b+1)+P(b+1) [U(b,b+j) E(b+1,b+j)]_{j=2..} U(b,NB)
+//         (the warp that finishes U(b,b+1) factors the next diagonal block itself: measured, ANY queueing delay of P
+//         stalls the solves of the next macro column -- 4 slots later: -12 % at n = 1024)
 // Every task's prerequisites precede it in the queue, so a warp that waits is always waiting for a task another warp
 // is already running: no deadlock.
 #include "fastmath.cuh"
@@ -526,7 +528,7 @@ __global__ void __launch_bounds__(LW * 32, CPS) krig_nll_flow_kernel(const NllAr
     double* const tiles = a.workspace + (size_t)blockIdx.x * flow_ws_doubles(G.NT);
     double* const wring = dyn_s + (size_t)wid * (ST * 8 * 64);
     for (int j = threadIdx.x; j < E2TAB; j += blockDim.x) S.etab[j] = g_e2tab[j];
-    const int total_tasks = NB * NB + 2 * NB;
+    const int total_tasks = NB * NB + NB + 1;
     const size_t ntri = (size_t)G.NT * (G.NT + 1) / 2;
 
     for (int iter = 0;; ++iter) {
@@ -588,59 +590,42 @@ __global__ void __launch_bounds__(LW * 32, CPS) krig_nll_flow_kernel(const NllAr
                 b = 0;
                 g = (t <= 1) ? 0 : t - 1;
             } else {
-                int l = t - (NB + 1), cb = 0;
-                while (true) {
-                    const int m = NB - cb - 1;
-                    const int cnt = (m >= 1) ? 2 * m + 2 : 1;
-                    if (l < cnt) break;
-                    l -= cnt;
-                    ++cb;
-                }
+                // macro column cb < NB - 1 owns 2 (NB - cb) - 1 queue slots, cb (2 NB - cb) precede it
+                int l = t - (NB + 1);
+                int cb = (int)((float)NB - sqrtf((float)(NB * NB - l)));
+                cb = max(0, min(cb, NB - 1));
+                while (cb > 0 && cb * (2 * NB - cb) > l) --cb;
+                while (cb < NB - 1 && (cb + 1) * (2 * NB - cb - 1) <= l) ++cb;
+                l -= cb * (2 * NB - cb);
                 const int m = NB - cb - 1;
-                if (m < 1 || l == 2 * m + 1) {
+                if (m < 1 || l == 2 * m) {
                     kind = 2, b = cb, g = NB;
                 } else if (l == 0) {
                     kind = 0, b = cb + 1, g = cb + 1;
                 } else if (l == 1) {
                     kind = 2, b = cb, g = cb + 1;
-                } else if (l == 2) {
-                    kind = 1, b = cb + 1, g = cb + 1;
                 } else {
-                    const int j = 2 + ((l - 3) >> 1);
-                    if (((l - 3) & 1) == 0) kind = 2, b = cb, g = cb + j;
+                    const int j = 2 + ((l - 2) >> 1);
+                    if (((l - 2) & 1) == 0) kind = 2, b = cb, g = cb + j;
                     else kind = 0, b = cb + 1, g = cb + j;
                 }
             }
             FPH_MARK(0);
-            const bool failed = *(volatile int*)&S.failed != 0;
             if (kind == 0) {
-                if (!failed) flow_task_e<MODE>(S, a, tiles, b, g, lane);
+                if (*(volatile int*)&S.failed == 0) flow_task_e<MODE>(S, a, tiles, b, g, lane);
                 FPH_MARK(12);
                 __threadfence_block();
                 __syncwarp();
                 wait_ge(&S.erow[g], b);  // keep the per-row counter monotonic
                 if (lane == 0) *(volatile int*)&S.erow[g] = b + 1;
                 FPH_MARK(13);
-            } else if (kind == 1) {
-                if (b > 0) wait_ge(&S.rowdone[b], b);
-                FPH_MARK(1);
-                const bool failed2 = *(volatile int*)&S.failed != 0;
-                bool ok = true;
-                double logsum = 0.0;
-                if (!failed2) ok = flow_task_p<ST>(S, a, tiles, wring, b, lane, logsum, fph_t);
-                __syncwarp();
-                if (lane == 0) {
-                    if (!failed2 && ok) S.logacc += logsum;
-                    if (!ok) *(volatile int*)&S.failed = 1;
-                    __threadfence_block();
-                    *(volatile int*)&S.pdone = b + 1;
-                }
-            } else {
+                continue;
+            }
+            if (kind == 2) {
                 wait_ge(&S.rowdone[b], b);  // the B strip; P(b) itself is awaited right before the solve
                 wait_ge(&S.rowdone[g], b);
                 FPH_MARK(7);
-                const bool failed2 = *(volatile int*)&S.failed != 0;
-                if (!failed2) {
+                if (*(volatile int*)&S.failed == 0) {
                     if (g < NB) flow_task_u<4, ST>(S, a, tiles, wring, b, g, lane, fph_t);
                     else flow_task_u<1, ST>(S, a, tiles, wring, b, g, lane, fph_t);
                 }
@@ -649,6 +634,27 @@ __global__ void __launch_bounds__(LW * 32, CPS) krig_nll_flow_kernel(const NllAr
                 if (lane == 0) {
                     *(volatile int*)&S.rowdone[g] = b + 1;
                     atomicAdd(&S.coldone[b], 1);
+                }
+                // The warp that finishes U(b,b+1) has just produced the last input of the next diagonal block: it
+                // factors it right away (a queued P task only made another warp sleep until this point, and any
+                // delay of P stalls every solve of the next macro column).
+                if (g != b + 1 || g >= NB) continue;
+                b = g;
+            }
+            // P(b)
+            if (b > 0) wait_ge(&S.rowdone[b], b);
+            FPH_MARK(1);
+            {
+                const bool failed = *(volatile int*)&S.failed != 0;
+                bool ok = true;
+                double logsum = 0.0;
+                if (!failed) ok = flow_task_p<ST>(S, a, tiles, wring, b, lane, logsum, fph_t);
+                __syncwarp();
+                if (lane == 0) {
+                    if (!failed && ok) S.logacc += logsum;
+                    if (!ok) *(volatile int*)&S.failed = 1;
+                    __threadfence_block();
+                    *(volatile int*)&S.pdone = b + 1;
                 }
             }
         }
@@ -787,7 +793,7 @@ cudaError_t launch_nll_flow(NllArgs a, int mode, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     static const int cfg = [] { const char* v = getenv("SMB_FLOW_CFG"); return v ? atoi(v) : 0; }();
     // bit 0: evict_first on the A strips; bits 4..: L2 prefetch distance in k-steps (0 = off)
-    static const int l2 = [] { const char* v = getenv("SMB_FLOW_L2"); return v ? atoi(v) : 1 + 16 * 8; }();
+    static const int l2 = [] { const char* v = getenv("SMB_FLOW_L2"); return v ? atoi(v) : 1; }();
     a.l2mode = l2;
     const int NT = a.npad / 8;
     int sel = cfg ? cfg : (NT < 96 ? 42 : 63);  // 4 warps x 4 CTAs below n = 768, 6 warps x 2 CTAs (168 registers) above

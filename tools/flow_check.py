@@ -101,13 +101,13 @@ def main():
     quick = '--quick' in sys.argv
     parity = [(136, 2, 8), (200, 3, 8), (256, 8, 8), (300, 8, 8), (520, 4, 8), (1024, 8, 6)]
     grid = [(200, 2, 3, 2)]
-    timing = [(136, 8, 9472), (192, 8, 9472), (256, 8, 9472), (320, 8, 4736), (384, 8, 4736), (512, 2, 2368), (768, 8, 1184), (2048, 8, 296)]
+    timing = [(384, 8, 4736), (512, 8, 2368), (768, 8, 1184), (1024, 8, 1184), (2048, 8, 296)]
     if quick:
         timing = [(256, 8, 2368), (512, 8, 1184), (1024, 8, 592)]
     configs = []
-    configs.append(('v1 macro-panel', {'SMB_LARGE_V1': '1'}, False))
-    for cfg in ('42', '43', '63', '83'):
-        configs.append((f'flow cfg {cfg}', {'SMB_FLOW_CFG': cfg, 'SMB_FLOW_L2': '1'}, False))
+    configs.append(('flow default', {}, True))
+    for cfg in ('42', '63'):
+        configs.append((f'flow cfg {cfg}', {'SMB_FLOW_CFG': cfg}, False))
 
     for name, env, with_parity in configs:
         spec = {'timing': timing}
