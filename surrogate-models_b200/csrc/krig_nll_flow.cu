@@ -215,21 +215,21 @@ __device__ __forceinline__ void flow_task_e(const FlowCtl& S, const NllArgs& a, 
             ++ce;
         }
     };
+    // ONE copy of the chunk evaluation in the loop body (three unrolled copies made it 18 KB: larger than the
+    // instruction cache of a scheduler, and `no_instruction` became the top stall reason at n = 512); the three
+    // buffers rotate through register moves instead.
     const int total = ntile * nch;
     double2 b0[4], b1[4], b2[4];
     issue(b0);
     issue(b1);
 #pragma unroll 1
-    for (int x = 0; x < total; x += 3) {
+    for (int x = 0; x < total; ++x) {
         issue(b2);
         consume(b0);
-        if (x + 1 < total) {
-            issue(b0);
-            consume(b1);
-        }
-        if (x + 2 < total) {
-            issue(b1);
-            consume(b2);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            b0[u] = b1[u];
+            b1[u] = b2[u];
         }
     }
 }
@@ -368,15 +368,18 @@ __device__ __forceinline__ void flow_task_u(FlowCtl& S, const NllArgs& a, double
     if (*(volatile int*)&S.failed != 0) return;
     // X = C L_bb^-T by block forward substitution over the 4 tile columns, in place in the scratch:
     //   T_jj = C_jj + sum_{m<jj} X_m (-L_jj,m)^T ,  X_jj = T_jj W_jj^T     (slot (ii, jj): C -> T -> X)
+    // (runtime loops over jj / m: unrolled, this epilogue was 870 instructions executed once per task -- pure
+    // instruction-cache traffic)
     const double* Wb = S.W[b & 1];
-#pragma unroll
+#pragma unroll 1
     for (int jj = 0; jj < 4; ++jj) {
         double t[HI][2];
 #pragma unroll
         for (int ii = 0; ii < HI; ++ii) ld_acc(scr + (ii * 4 + jj) * 64, lane, t[ii][0], t[ii][1]);
-#pragma unroll
+        const double* Wrow = Wb + (jj * (jj + 1) / 2) * 64;
+#pragma unroll 1
         for (int m = 0; m < jj; ++m) {
-            const double2 nl = ld_frag(Wb + (jj * (jj + 1) / 2 + m) * 64, lane);
+            const double2 nl = ld_frag(Wrow + m * 64, lane);
 #pragma unroll
             for (int ii = 0; ii < HI; ++ii) {
                 const double2 xf = ld_frag(scr + (ii * 4 + m) * 64, lane);
@@ -389,7 +392,7 @@ __device__ __forceinline__ void flow_task_u(FlowCtl& S, const NllArgs& a, double
             for (int ii = 0; ii < HI; ++ii) st_acc(scr + (ii * 4 + jj) * 64, lane, t[ii][0], t[ii][1]);
         }
         __syncwarp();
-        const double2 w = ld_frag(Wb + (jj * (jj + 1) / 2 + jj) * 64, lane);
+        const double2 w = ld_frag(Wrow + jj * 64, lane);
         double2 tf[HI];
 #pragma unroll
         for (int ii = 0; ii < HI; ++ii) tf[ii] = ld_frag(scr + (ii * 4 + jj) * 64, lane);
@@ -781,8 +784,10 @@ bool nll_uses_flow(int n) {
         return (v && v[0] == '1') || (g && g[0] == '1');
     }();
     const int NT = (n + 7) / 8;
-    // measured crossover against the macro-panel kernel (tools/flow_check.py): n = 320: 6.9 vs 7.0, n = 384: 8.0 vs 7.9
-    return !v1 && NT > 44 && (NT + 3) / 4 + 2 <= FLOW_MAXG;
+    // measured crossover against the macro-panel kernel (tools/flow_check.py, k = 8): n = 136: 2.6 vs 3.1 TFLOP/s,
+    // n = 160: 4.1 vs 3.8, n = 256: 6.5 vs 5.9, n = 1024: 16.7 vs 13.5
+    static const int lo = [] { const char* v = getenv("SMB_FLOW_MIN_NT"); return v ? atoi(v) : 18; }();  // tuning
+    return !v1 && NT > lo && (NT + 3) / 4 + 2 <= FLOW_MAXG;
 }
 
 cudaError_t launch_nll_flow(NllArgs a, int mode, cudaStream_t st) {
@@ -796,8 +801,10 @@ cudaError_t launch_nll_flow(NllArgs a, int mode, cudaStream_t st) {
     static const int l2 = [] { const char* v = getenv("SMB_FLOW_L2"); return v ? atoi(v) : 1; }();
     a.l2mode = l2;
     const int NT = a.npad / 8;
-    int sel = cfg ? cfg : (NT < 96 ? 42 : 63);  // 4 warps x 4 CTAs below n = 768, 6 warps x 2 CTAs (168 registers) above
+    int sel = cfg ? cfg : (NT < 192 ? 42 : 63);  // 4 warps x 4 CTAs below n = 1536, 6 warps x 2 CTAs (168 registers) above
     switch (sel) {
+        case 22: return launch_flow_t<2, 2, 6>(a, mode, st);   // 12 warps / SM in 6 CTAs
+        case 32: return launch_flow_t<3, 2, 5>(a, mode, st);   // 15 warps / SM in 5 CTAs
         case 42: return launch_flow_t<4, 2, 4>(a, mode, st);
         case 43: return launch_flow_t<4, 3, 3>(a, mode, st);   // 12 warps / SM, 168 registers
         case 63: return launch_flow_t<6, 3, 2>(a, mode, st);   // 12 warps / SM, 168 registers

@@ -214,10 +214,10 @@ def test_c3_n1024_k8(gold, K):
     assert np.max(rel(yy, yr)) < 1e-8 and np.max(np.abs(mse - mr)) < 1e-8 * k._fit['sigma2']
 
 
-@pytest.mark.parametrize('n,k_', [(1, 1), (2, 1), (7, 2), (13, 3), (65, 2), (73, 2), (129, 4), (225, 3), (230, 16)])
+@pytest.mark.parametrize('n,k_', [(1, 1), (2, 1), (7, 2), (13, 3), (65, 2), (73, 2), (129, 4), (144, 2), (225, 3), (230, 16)])
 def test_ragged_sizes_against_oracle(K, n, k_):
-    """sizes straddling every kernel variant / padding boundary (8-tiles; n <= 72 warp-per-candidate,
-    <= 224 CTA in shared memory, beyond: global-memory tiles)"""
+    """sizes straddling every kernel variant / padding boundary (8-tiles; n <= 64 warp-per-candidate, <= 128 CTA in
+    shared memory, <= 144 macro-panel kernel, beyond: dataflow kernel)"""
     rng = np.random.default_rng(n * 100 + k_)
     X = rng.uniform(0, 10, (n, k_))
     y = np.sin(X.sum(axis=1)) + 0.1 * X[:, 0] ** 2
@@ -517,9 +517,9 @@ def test_large_n_and_large_k(K):
     assert check_values(nll16, ref16, cond16, cond_max=1e12) == 6
 
 
-@pytest.mark.parametrize('n,k_', [(353, 2), (361, 5), (377, 16), (500, 3), (520, 1)])
+@pytest.mark.parametrize('n,k_', [(145, 3), (353, 2), (361, 5), (377, 16), (500, 3), (520, 1)])
 def test_dataflow_kernel_ragged_sizes(K, n, k_):
-    """n > 352 runs on the dataflow kernel (krig_nll_flow.cu): tile counts NT = 45, 46, 48, 63, 65 cover every
+    """n > 144 runs on the dataflow kernel (krig_nll_flow.cu): tile counts NT = 45, 46, 48, 63, 65 cover every
     remainder of the 4-tile row groups / macro columns, k = 1 .. 16 every chunking of the entry evaluation"""
     rng = np.random.default_rng(n * 100 + k_)
     X = rng.uniform(0, 10, (n, k_))
