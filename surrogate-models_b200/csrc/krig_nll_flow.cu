@@ -217,20 +217,16 @@ __device__ __forceinline__ void flow_task_e(const FlowCtl& S, const NllArgs& a, 
     };
     // ONE copy of the chunk evaluation in the loop body (three unrolled copies made it 18 KB: larger than the
     // instruction cache of a scheduler, and `no_instruction` became the top stall reason at n = 512); the three
-    // buffers rotate through register moves instead.
+    // buffers rotate through register moves instead (two buffers: one chunk of loads in flight is enough, measured).
     const int total = ntile * nch;
-    double2 b0[4], b1[4], b2[4];
+    double2 b0[4], b1[4];
     issue(b0);
-    issue(b1);
 #pragma unroll 1
     for (int x = 0; x < total; ++x) {
-        issue(b2);
+        issue(b1);
         consume(b0);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            b0[u] = b1[u];
-            b1[u] = b2[u];
-        }
+        for (int u = 0; u < 4; ++u) b0[u] = b1[u];
     }
 }
 
