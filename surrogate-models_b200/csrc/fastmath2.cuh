@@ -11,7 +11,7 @@
 // 9 fp64-pipe instructions per power (exp_unguarded of fastmath.cuh: 12 + the p * ln|dx| multiply) and the
 // accumulation s += theta' * |dx|^p is one more fma (theta' = theta * log2 e, so R = 2^(-s)).
 // Checked against long-double libm on the host (tests/test_host_logic.py::test_exp2_core_emulation builds
-// tools/exp2_check.c from the same constants): max 0.52 ulp + the rounding of the table argument.
+// tools/exp2_check.c from the same constants): max 1.01 ulp (table entry 0.5 + final rounding 0.5).
 #pragma once
 #include <cuda_runtime.h>
 

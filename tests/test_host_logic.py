@@ -168,3 +168,26 @@ def test_validation_with_opaque_callable(gold):
     assert abs(v.calc_deviation(vx, vy, f) - np.mean(np.abs(vy - pred)) / vy.mean()) < 1e-14
     assert np.allclose(v.calc_rae(vx, vy, f), np.abs((vy - pred) / vy), rtol=0, atol=1e-14)
     assert ValidationResults().press == 0.
+
+
+def test_exp2_core_emulation(tmp_path):
+    """csrc/fastmath2.cuh (base-2 table-driven power / exponential of the n > 144 likelihood kernel) emulated on the
+    host with the same constants and operation order (tools/exp2_check.c, C99 fma) against long-double libm"""
+    import json
+    import shutil
+    import subprocess
+    if shutil.which('gcc') is None:
+        pytest.skip('gcc not available')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / 'exp2_check')
+    subprocess.run(['gcc', '-O2', '-std=gnu99', '-ffp-contract=off', os.path.join(root, 'tools', 'exp2_check.c'), '-lm', '-o', exe],
+                   check=True)
+    out = json.loads(subprocess.run([exe], check=True, capture_output=True, text=True).stdout)
+    assert out['pow2_fast_max_ulp'] < 1.1 and out['exp2_neg_max_ulp'] < 1.1
+    assert out['zero_dist'] < 1e-100 and out['padding'] > 1e200          # |dx| = 0 -> 0, padding -> "infinity"
+    assert out['exp2_neg_0'] == 1.0 and out['exp2_neg_1100'] == 0.0 and out['exp2_neg_inf'] == 0.0
+    # the kernel's constants are the ones the emulation uses
+    hdr = open(os.path.join(root, 'surrogate-models_b200', 'csrc', 'fastmath2.cuh')).read()
+    src = open(os.path.join(root, 'tools', 'exp2_check.c')).read()
+    for c in ('1.3538030870311431e-03', '9.163913992275266e-07', '4.135378350676714e-10', '1.399621994296973e-13'):
+        assert c in hdr and c in src
