@@ -803,7 +803,10 @@ cudaError_t launch_nll_flow(NllArgs a, int mode, cudaStream_t st) {
         case 32: return launch_flow_t<3, 2, 5>(a, mode, st);   // 15 warps / SM in 5 CTAs
         case 42: return launch_flow_t<4, 2, 4>(a, mode, st);
         case 43: return launch_flow_t<4, 3, 3>(a, mode, st);   // 12 warps / SM, 168 registers
+        case 52: return launch_flow_t<5, 2, 3>(a, mode, st);   // 15 warps / SM, 136 registers
         case 63: return launch_flow_t<6, 3, 2>(a, mode, st);   // 12 warps / SM, 168 registers
+        case 72: return launch_flow_t<7, 2, 2>(a, mode, st);   // 14 warps / SM, 144 registers
+        case 73: return launch_flow_t<7, 3, 2>(a, mode, st);
         case 64: return launch_flow_t<6, 4, 2>(a, mode, st);
         case 82: return launch_flow_t<8, 2, 2>(a, mode, st);
         default: return launch_flow_t<8, 3, 2>(a, mode, st);
