@@ -24,8 +24,17 @@ for _p in (ROOT, os.path.join(ROOT, 'surrogate-models_b200')):
 
 import numpy as np  # noqa: E402
 
-# keep stdout to the single JSON line: NCCL's version / INFO banner goes to stderr
+# keep stdout to the single JSON line: NCCL prints its version banner to file descriptor 1 from C (seen on the 2-GPU
+# box even with NCCL_DEBUG_FILE set), so fd 1 is pointed at stderr for the whole run and the JSON line is written to
+# the saved descriptor at the end
 os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + '\n').encode())
 
 N_SAMPLES, K_DIM, T_SEC, CAND_PER_GPU = 64, 2, 40, 1000000
 METRIC = 'kriging likelihood evaluations/s (n=64, k=2)'
@@ -128,7 +137,7 @@ def run_reference(args):
         'e2e': {'value': value, 'unit': 'evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -394,7 +403,7 @@ def run_gpu(args):
             'cpu_baseline': cpu, 'secondary': secondary, 'secondary_c3': secondary_c3, 'secondary_c4': secondary_c4,
             'result': {'best_idx': best_idx, 'best_nll': best_val},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         td.destroy_process_group()
     return 0
