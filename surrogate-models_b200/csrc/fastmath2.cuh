@@ -14,6 +14,7 @@
 // tools/exp2_check.c from the same constants): max 1.01 ulp (table entry 0.5 + final rounding 0.5).
 #pragma once
 #include <cuda_runtime.h>
+#include <cmath>
 
 namespace smb {
 
@@ -59,5 +60,35 @@ __device__ __forceinline__ double exp2_neg(double s, const double* __restrict__ 
     v = (s < -1023.0) ? INFINITY : v;
     return v;
 }
+
+
+// 2^(-c s) for s >= 0 with the scale folded into the range reduction: c512 = 512 c (c > 0), smax = 1021 / c.
+// (gaussian RBF: exp(-(a r)^2) = 2^(-(a^2 log2 e) r^2), one fp64 instruction less than scaling first)
+__device__ __forceinline__ double exp2_neg_scaled(double s, double c512, double smax, const double* __restrict__ tab) {
+    const double MAGIC = 6755399441055744.0;
+    const double t = fma(s, -c512, MAGIC);
+    const double nf = t - MAGIC;
+    const double r = fma(s, -c512, -nf);
+    const double v = exp2_core(t, r, tab);
+    return (s > smax) ? 0.0 : v;
+}
+
+// 2^(j/512), correctly rounded on the host; one copy per translation unit (no relocatable device code in this build),
+// uploaded once per device by upload_e2tab() of the same translation unit and copied into shared memory by the kernels
+namespace {
+__device__ double g_e2tab[E2TAB];
+inline cudaError_t upload_e2tab() {
+    static int done_for = -1;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev == done_for) return cudaSuccess;
+    double h[E2TAB];
+    for (int j = 0; j < E2TAB; ++j) h[j] = (double)exp2l((long double)j / E2TAB);
+    e = cudaMemcpyToSymbol(g_e2tab, h, sizeof(h));
+    if (e == cudaSuccess) done_for = dev;
+    return e;
+}
+}  // namespace
 
 }  // namespace smb

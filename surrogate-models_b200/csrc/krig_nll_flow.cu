@@ -59,8 +59,6 @@ extern "C" int smb_flow_phase_read(unsigned long long* out, int reset) {
 
 constexpr int FLOW_MAXG = 130;  // row groups incl. the right-hand-side group: n <= 4096
 
-__device__ double g_e2tab[E2TAB];  // 2^(j/512), correctly rounded on the host (launch_nll_flow)
-
 struct FlowCtl {
     double etab[E2TAB];
     double W[2][10 * 64];  // factor of the diagonal block of macro column b in slot b & 1 (see P / U)
@@ -729,19 +727,6 @@ cudaError_t launch_dtab_packed(const double* X, int n, int k, int npad, const do
     if (grid > 148 * 16) grid = 148 * 16;
     dtab_packed_kernel<<<grid, 256, 0, st>>>(X, n, k, ntri, p_axis, P, D);
     return cudaGetLastError();
-}
-
-static cudaError_t upload_e2tab() {
-    static int done_for = -1;
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    if (dev == done_for) return cudaSuccess;
-    double h[E2TAB];
-    for (int j = 0; j < E2TAB; ++j) h[j] = (double)exp2l((long double)j / E2TAB);
-    e = cudaMemcpyToSymbol(g_e2tab, h, sizeof(h));
-    if (e == cudaSuccess) done_for = dev;
-    return e;
 }
 
 template <int LW, int ST, int CPS>

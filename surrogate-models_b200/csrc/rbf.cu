@@ -10,6 +10,7 @@
 #include <cooperative_groups.h>
 
 #include "fastmath.cuh"
+#include "fastmath2.cuh"
 #include "tile_chol.cuh"
 #include "kernels.h"
 
@@ -384,8 +385,11 @@ __global__ void __launch_bounds__(256) rbf_predict_kernel(const double* __restri
     extern __shared__ __align__(16) double smem[];
     double* X_s = smem;                          // [chunk][k]
     double* c_s = X_s + (size_t)RBF_CHUNK * k;   // [chunk]
-    __shared__ double etab[EXP_TAB];
-    exp_table_init(etab, threadIdx.x, blockDim.x);
+    __shared__ double etab[E2TAB];
+    for (int j = threadIdx.x; j < E2TAB; j += blockDim.x) etab[j] = g_e2tab[j];
+    // gaussian: e^-(a r)^2 = 2^-(c r^2), c = a^2 log2 e, folded into the range reduction of the base-2 exponential
+    const double c512 = 512.0 * (a * a) * 1.4426950408889634;
+    const double smax = (c512 > 0.0) ? 1021.0 * 512.0 / c512 : INFINITY;
     const int kk = KD > 0 ? KD : k;
     const long long Q = (long long)gridDim.x * blockDim.x;
     const long long nrounds = (Nq + Q - 1) / Q;
@@ -407,12 +411,12 @@ __global__ void __launch_bounds__(256) rbf_predict_kernel(const double* __restri
 #pragma unroll
                 for (int d = 0; d < kk; ++d) {
                     const double dx = xq[d] - X_s[(size_t)i * k + d];
-                    s = __dadd_rn(s, __dmul_rn(dx, dx));
+                    s = fma(dx, dx, s);
                 }
                 double phi;
-                if (kind == 2) {  // gaussian: e^-(a r)^2 = e^-(a^2 s): no sqrt (the argument differs from the
-                    // reference's sqrt-then-square by <= 2 ulp, i.e. <= 1e-16 absolute on phi); table-driven exp
-                    phi = exp_fast<false>(-((a * a) * s), etab);
+                if (kind == 2) {  // gaussian: no sqrt (the argument differs from the reference's sqrt-then-square by a
+                    // few ulp, i.e. ~1e-16 absolute on phi); table-driven base-2 exponential, 9 fp64 instructions
+                    phi = exp2_neg_scaled(s, c512, smax, etab);
                 } else {
                     phi = rbf_phi(kind, a, sqrt(s));
                 }
@@ -426,12 +430,13 @@ __global__ void __launch_bounds__(256) rbf_predict_kernel(const double* __restri
 cudaError_t launch_rbf_predict(const double* X, int n, int k, int kind, double a, const double* coeff,
                                const double* Xq, long long Nq, double* y_out, cudaStream_t st, long long* launches) {
     if (Nq <= 0) return cudaSuccess;
+    cudaError_t e = upload_e2tab();
+    if (e != cudaSuccess) return e;
     const size_t smem = (size_t)RBF_CHUNK * (k + 1) * 8;
     long long grid = (Nq + 255) / 256;
     const long long per_sm = (long long)((size_t)(227 * 1024) / (smem + 1024));  // resident CTAs (shared-memory bound)
     const long long cap = (long long)sm_count() * (per_sm < 1 ? 1 : (per_sm > 6 ? 6 : per_sm));
     if (grid > cap) grid = cap;
-    cudaError_t e;
 #define SMB_RBF_LAUNCH(KD)                                                                                          \
     e = cudaFuncSetAttribute(rbf_predict_kernel<KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
     if (e != cudaSuccess) return e;                                                                                 \
