@@ -27,6 +27,8 @@
 //         stalls the solves of the next macro column -- 4 slots later: -12 % at n = 1024)
 // Every task's prerequisites precede it in the queue, so a warp that waits is always waiting for a task another warp
 // is already running: no deadlock.
+// Tuning knobs (environment, read once): SMB_FLOW_CFG = 42 | 43 | 63 | 73 (warps per CTA, ring depth), SMB_FLOW_L2
+// (bit 0: evict_first on the A strips, bits 4..: L2 prefetch distance), SMB_FLOW_MIN_NT (smallest tile count routed here).
 #include "fastmath.cuh"
 #include "fastmath2.cuh"
 #include "tile_chol.cuh"
@@ -783,18 +785,11 @@ cudaError_t launch_nll_flow(NllArgs a, int mode, cudaStream_t st) {
     a.l2mode = l2;
     const int NT = a.npad / 8;
     int sel = cfg ? cfg : (NT < 192 ? 42 : 63);  // 4 warps x 4 CTAs below n = 1536, 6 warps x 2 CTAs (168 registers) above
-    switch (sel) {
-        case 22: return launch_flow_t<2, 2, 6>(a, mode, st);   // 12 warps / SM in 6 CTAs
-        case 32: return launch_flow_t<3, 2, 5>(a, mode, st);   // 15 warps / SM in 5 CTAs
+    switch (sel) {  // (2 .. 7 warps per CTA at 12 - 16 warps per SM all measured within 5 % of each other)
         case 42: return launch_flow_t<4, 2, 4>(a, mode, st);
         case 43: return launch_flow_t<4, 3, 3>(a, mode, st);   // 12 warps / SM, 168 registers
-        case 52: return launch_flow_t<5, 2, 3>(a, mode, st);   // 15 warps / SM, 136 registers
-        case 63: return launch_flow_t<6, 3, 2>(a, mode, st);   // 12 warps / SM, 168 registers
-        case 72: return launch_flow_t<7, 2, 2>(a, mode, st);   // 14 warps / SM, 144 registers
-        case 73: return launch_flow_t<7, 3, 2>(a, mode, st);
-        case 64: return launch_flow_t<6, 4, 2>(a, mode, st);
-        case 82: return launch_flow_t<8, 2, 2>(a, mode, st);
-        default: return launch_flow_t<8, 3, 2>(a, mode, st);
+        case 73: return launch_flow_t<7, 3, 2>(a, mode, st);   // 14 warps / SM, 144 registers
+        default: return launch_flow_t<6, 3, 2>(a, mode, st);   // 63: 12 warps / SM, 168 registers
     }
 }
 

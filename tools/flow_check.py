@@ -106,7 +106,7 @@ def main():
         timing = [(256, 8, 2368), (512, 8, 1184), (1024, 8, 592)]
     configs = []
 
-    for cfg in ('42', '52', '63', '72', '73'):
+    for cfg in ('42', '43', '63', '73'):
         configs.append((f'flow cfg {cfg}', {'SMB_FLOW_CFG': cfg, 'SMB_FLOW_MIN_NT': '16'}, False))
 
     for name, env, with_parity in configs:
