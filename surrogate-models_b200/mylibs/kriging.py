@@ -19,6 +19,7 @@ from myutils.time_track import TimeTrack
 from sm_b200 import _cabi, device, dist
 
 VERBOSE = False
+LAZY_FIT_MIN_N = 145  # from here on the optimiser objective is one single-candidate launch of the batched kernel
 
 
 class Kriging:
@@ -42,6 +43,7 @@ class Kriging:
         # device state (created on first use)
         self._d = None
         self._fit = None
+        self._fit_stale = False  # parameters changed through the optimiser objective: fit deferred (n >= LAZY_FIT_MIN_N)
         self._cor_mat_cache = None
         self._cor_mat_inv_cache = None
 
@@ -94,20 +96,42 @@ class Kriging:
         self._cor_mat_cache = None
         self._cor_mat_inv_cache = None
         self._fit = self._run_fit()
+        self._fit_stale = False
         if not self._fit['ok'] and VERBOSE:
             print('ERROR: correlation matrix is not numerically positive definite')
 
+    def _ensure_fit(self):
+        """(Re)runs the fit when there is none yet or the optimiser objective left it behind the parameters."""
+        if self._fit is None or self._fit_stale:
+            self._calc_cormat()
+            self._mu = np.float64(self._fit['mu'])
+
+    def _objective_nll(self, theta, p):
+        """update_param + calc_likelihood for the optimiser objectives (kriging.py:118-141).  For n >= LAZY_FIT_MIN_N
+        the likelihood comes from ONE single-candidate launch of the batched kernel and the full fit (weights,
+        L^-1 for the MSE: 18 ms at n = 1024) is deferred until something reads the fitted state -- SLSQP makes ~100
+        sequential objective calls.  Smaller n keeps the fit-per-call path (tens of microseconds)."""
+        if self._n < LAZY_FIT_MIN_N:
+            self.update_param(theta, p)
+            return self.calc_likelihood()
+        self._theta = np.array(theta, dtype=np.float64)
+        self._p = np.array(p, dtype=np.float64)
+        self._cor_mat_cache = None
+        self._cor_mat_inv_cache = None
+        self._fit_stale = True
+        nll = self._likelihood_list(self._theta.reshape(1, -1), self._p.reshape(1, -1))[0][0]
+        return float('inf') if np.isnan(nll) else np.float64(nll)
+
     def _calc_mu(self):
         """mu = 1^T R^-1 y / 1^T R^-1 1 (reference: kriging.py:86-93); computed by the fit kernel."""
-        if self._fit is None:
-            self._calc_cormat()
+        self._ensure_fit()
         self._mu = np.float64(self._fit['mu'])
         return self._mu
 
     @property
     def _cor_mat(self):
         """Dense correlation matrix (reference attribute, kriging.py:80); None before update_param."""
-        if self._fit is None:
+        if self._fit is None and not self._fit_stale:
             return None
         if self._cor_mat_cache is None:
             self._cor_mat_cache = self._run_fit(want_R=True)['R'].cpu().numpy()
@@ -117,8 +141,9 @@ class Kriging:
     def _core_mat_inv(self):
         """R^-1 = L^-T L^-1 assembled on the device from the cached factor (reference attribute,
         kriging.py:79).  Compatibility accessor, not on the hot path."""
-        if self._fit is None:
+        if self._fit is None and not self._fit_stale:
             return None
+        self._ensure_fit()
         if self._cor_mat_inv_cache is None:
             import torch
             n = self._n
@@ -142,8 +167,7 @@ class Kriging:
         negative concentrated log-likelihood at the current parameters (reference: kriging.py:95-116)
         :return: neg. log. likelihood, or inf when R is not numerically SPD / sigma^2 is invalid
         """
-        if self._fit is None:
-            self._calc_cormat()
+        self._ensure_fit()
         nll = self._fit['nll']
         if np.isnan(nll):
             return float('inf')
@@ -151,13 +175,11 @@ class Kriging:
 
     def _calc_likelihood_opti_theta_only(self, params, *args):
         """(reference: kriging.py:118-121)"""
-        self.update_param(params, args[0])
-        return self.calc_likelihood()
+        return self._objective_nll(params, args[0])
 
     def _calc_likelihood_opti(self, params, *args):
         """(reference: kriging.py:123-128)"""
-        self.update_param(params[0:self._k], params[self._k:])
-        neg_ln_like = self.calc_likelihood()
+        neg_ln_like = self._objective_nll(params[0:self._k], params[self._k:])
         if getattr(self, 'records', None) is not None:
             self.records.append(params)
         return neg_ln_like
@@ -170,8 +192,7 @@ class Kriging:
         thetas = []
         for e in exps:
             thetas.append(10.**e)
-        self.update_param(thetas, params[self._k:])
-        neg_ln_like = self.calc_likelihood()
+        neg_ln_like = self._objective_nll(thetas, params[self._k:])
         if getattr(self, 'records', None) is not None:
             self.records.append(params)
         return neg_ln_like
@@ -252,19 +273,26 @@ class Kriging:
         C = e.shape[0]
         if C == 0:
             return (np.empty(0), float('inf'), -1) if return_best else np.empty(0)
-        theta = device.to_dev(np.power(10., e))  # 10.**e, vectorised
-        pd = device.to_dev(q)
+        out, bv, bi = self._likelihood_list(np.power(10., e), q)  # 10.**e, vectorised
+        nanrow = np.isnan(e).any(axis=1) | np.isnan(q).any(axis=1)
+        out[nanrow] = np.nan  # NaN parameters -> NaN (kriging.py:131-132)
+        if return_best:
+            return out, bv, bi
+        return out
+
+    def _likelihood_list(self, theta_lin, p):
+        """sm_krig_nll_batch on linear theta[C,k], p[C,k] -> (nll[C], best value, best index)"""
+        L = _cabi.lib()
+        d = self._dev()
+        C = theta_lin.shape[0]
+        theta = device.to_dev(theta_lin)
+        pd = device.to_dev(p)
         nll = device.empty(C)
         bv, bi = device.empty(1), device.empty(1, dtype=_int64())
         _cabi.check(L.sm_krig_nll_batch(device.ptr(d['X']), device.ptr(d['y']), self._n, self._k, device.ptr(theta),
                                         device.ptr(pd), C, 0, device.ptr(nll), device.ptr(bv), device.ptr(bi),
                                         device.stream()))
-        out = nll.cpu().numpy()
-        nanrow = np.isnan(e).any(axis=1) | np.isnan(q).any(axis=1)
-        out[nanrow] = np.nan  # NaN parameters -> NaN (kriging.py:131-132)
-        if return_best:
-            return out, float(bv.item()), int(bi.item())
-        return out
+        return nll.cpu().numpy(), float(bv.item()), int(bi.item())
 
     def likelihood_grid(self, theta_sections=8, p_sections=5, c_begin=0, c_count=None, return_nll=True):
         """nll over candidates [c_begin, c_begin + c_count) of LikeliOptimizer.generate_grid's enumeration
@@ -304,8 +332,9 @@ class Kriging:
     def predict_batch(self, x_query, return_mse=False):
         """Mean (and ordinary-Kriging MSE) at many query points: Xq[Nq,k] -> y[Nq] (, mse[Nq]).
         Replaces a Python loop over Kriging.predict (kriging.py:206-220)."""
-        if self._fit is None:  # the reference predicts with whatever update_param left behind
+        if self._fit is None and not self._fit_stale:  # the reference predicts with whatever update_param left behind
             raise _cabi.SurrogateB200Error('predict before update_param / train: no fitted state')
+        self._ensure_fit()
         xq = np.asarray(x_query, dtype=np.float64)
         if xq.ndim == 1:
             xq = xq.reshape(-1, self._k)
@@ -317,6 +346,7 @@ class Kriging:
     def predict_device(self, xq_dev, return_mse=False):
         """predict_batch on a device tensor Xq[Nq,k]; results stay on the device (no sync)."""
         L = _cabi.lib()
+        self._ensure_fit()
         d, f = self._dev(), self._fit
         nq = xq_dev.shape[0]
         y = device.empty(nq)

@@ -605,6 +605,45 @@ print(json.dumps(dict(b=[float(v) for v in b])))
     assert np.max(rel(np.array(out['0']['b']), np.array(out['1']['b']))) < 1e-10   # cond ~1e4
 
 
+def test_lazy_objective_large_n(K):
+    """n >= 145: the optimiser objective is one single-candidate launch of the batched kernel and the full fit is
+    deferred; value and the state every accessor sees must equal update_param + calc_likelihood"""
+    import time
+    rng = np.random.default_rng(7)
+    X = rng.uniform(0, 10, (200, 2))
+    y = np.sin(X.sum(axis=1)) + 0.1 * X[:, 0] ** 2
+    params = np.array([-0.7, -0.4, 1.6, 1.3])
+    a = K(X, y)
+    a.records = None
+    v_lazy = a._calc_likelihood_opti_exp(params)
+    assert a._fit_stale and a._fit is None                    # nothing fitted yet
+    b = K(X, y)
+    b.update_param(10. ** params[:2], params[2:])
+    v_full = b.calc_likelihood()
+    assert rel(v_lazy, v_full) < 1e-10
+    xq = rng.uniform(0, 10, (16, 2))
+    assert np.max(rel(a.predict_batch(xq), b.predict_batch(xq))) < 1e-12      # predict triggers the deferred fit
+    assert not a._fit_stale and np.array_equal(a._theta, b._theta)
+    assert rel(a.calc_likelihood(), v_full) < 1e-12 and rel(a._mu, b._mu) < 1e-12
+    assert np.isnan(a._calc_likelihood_opti_exp(np.array([np.nan, 0., 1., 1.])))
+    # latency of one objective call at n = 1024, k = 8 (informative)
+    X3, y3 = workloads.c3_lhs1024()
+    c = K(X3, y3)
+    c.records = None
+    e3, p3 = workloads.c3_candidates(4, 8)
+    c._calc_likelihood_opti_exp(np.concatenate([e3[0], p3[0]]))
+    t0 = time.perf_counter()
+    for i in range(1, 4):
+        c._calc_likelihood_opti_exp(np.concatenate([e3[i], p3[i]]))
+    dt_lazy = (time.perf_counter() - t0) / 3
+    t0 = time.perf_counter()
+    c.update_param(10. ** e3[0], p3[0])
+    torch.cuda.synchronize()
+    dt_fit = time.perf_counter() - t0
+    print(f'objective call at n=1024: {dt_lazy * 1e3:.2f} ms (single-candidate launch) vs {dt_fit * 1e3:.2f} ms (full fit)')
+    assert dt_lazy < dt_fit
+
+
 def test_optimize_grid_end_to_end_r3(gold, K, capsys):
     """Kriging.optimize('grid') end to end on kriging_r3 (n = 36, k = 2): batched grid, then SciPy SLSQP on
     single evaluations exactly like the reference (likeli_optimizer.py:37-48).  The optimum sits at
