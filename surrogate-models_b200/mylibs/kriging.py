@@ -122,6 +122,34 @@ class Kriging:
         nll = self._likelihood_list(self._theta.reshape(1, -1), self._p.reshape(1, -1))[0][0]
         return float('inf') if np.isnan(nll) else np.float64(nll)
 
+    @property
+    def batched_stencil(self):
+        """LikeliOptimizer.find hands SciPy's finite-difference points of a gradient to _objective_map when the
+        objective is a single-candidate launch anyway (n >= LAZY_FIT_MIN_N): 2k sequential launches become one.
+        (At small n the per-call table set-up makes the batch slower than 2k fits -- measured)"""
+        return self._n >= LAZY_FIT_MIN_N
+
+    def _objective_map(self, fun, iterable):
+        """map-like `workers` callable for scipy.optimize.minimize (SciPy >= 1.16): the values of
+        _calc_likelihood_opti_exp at every point of `iterable`, from one batched launch.  `fun` (SciPy's wrapper of
+        the objective) is only used when a point is not a plain [log10 theta, p] vector."""
+        xs = [np.asarray(x, dtype=np.float64).ravel() for x in iterable]
+        if not xs:
+            return []
+        if any(x.shape[0] != 2 * self._k or np.isnan(x).any() for x in xs):
+            return [fun(x) for x in xs]
+        theta = np.array([[10. ** e for e in x[:self._k]] for x in xs])  # scalar pow, like the objective
+        p = np.array([x[self._k:] for x in xs])
+        nll = self._likelihood_list(theta, p)[0]
+        if getattr(self, 'records', None) is not None:
+            self.records.extend(xs)
+        # the object's parameters follow the last evaluated point, as after a sequential loop
+        self._theta, self._p = theta[-1].copy(), p[-1].copy()
+        self._cor_mat_cache = None
+        self._cor_mat_inv_cache = None
+        self._fit_stale = True
+        return [float('inf') if np.isnan(v) else np.float64(v) for v in nll]
+
     def _calc_mu(self):
         """mu = 1^T R^-1 y / 1^T R^-1 1 (reference: kriging.py:86-93); computed by the fit kernel."""
         self._ensure_fit()

@@ -34,6 +34,10 @@ class LikeliOptimizer:
             bnds.append((-5, +5))
         for i in range(0, dimensions):
             bnds.append((1., 2.))
+        owner = self._batched_owner(func)
+        if owner is not None and dimensions == owner._k and getattr(owner, 'batched_stencil', False):
+            # SciPy's own forward-difference stencil (same points, same steps), evaluated as ONE batched launch
+            opt['workers'] = owner._objective_map
         minima_res = minimize(func, guess, method='SLSQP', tol=1e-8, options=opt, bounds=bnds)
         if minima_res.nit >= self.maxIter:
             print('WARNING: max iter was used (LikeliOptimizer.py)')

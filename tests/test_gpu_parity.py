@@ -644,6 +644,39 @@ def test_lazy_objective_large_n(K):
     assert dt_lazy < dt_fit
 
 
+def test_batched_slsqp_stencil_large_n(K, capsys):
+    """n >= 145: LikeliOptimizer.find passes SciPy's forward-difference points to one batched launch (`workers`);
+    the optimisation path must be the one of the sequential objective: same end point, same iteration count"""
+    import time
+    from mylibs.likeli_optimizer import LikeliOptimizer
+    rng = np.random.default_rng(11)
+    X = rng.uniform(0, 10, (160, 2))
+    y = np.sin(X.sum(axis=1)) + 0.1 * X[:, 0] ** 2 + 0.05 * rng.standard_normal(160)
+
+    def run(batched):
+        k = K(X, y)
+        k.records = []
+        if not batched:
+            type(k).batched_stencil = property(lambda self: False)
+        try:
+            t0 = time.perf_counter()
+            res = LikeliOptimizer().find(k._calc_likelihood_opti_exp, 2)
+            dt = time.perf_counter() - t0
+        finally:
+            if not batched:
+                type(k).batched_stencil = orig
+        return res, dt, len(k.records)
+
+    orig = K.batched_stencil
+    rb, tb, nb = run(True)
+    rs, ts, ns = run(False)
+    capsys.readouterr()
+    assert rb.success == rs.success and rb.nit == rs.nit
+    assert np.array_equal(rb.x, rs.x) and rb.fun == rs.fun
+    assert nb == ns                                              # every evaluated point is recorded either way
+    print(f'SLSQP at n=160, k=2: {tb * 1e3:.0f} ms batched stencil vs {ts * 1e3:.0f} ms sequential, {rb.nit} iterations')
+
+
 def test_optimize_grid_end_to_end_r3(gold, K, capsys):
     """Kriging.optimize('grid') end to end on kriging_r3 (n = 36, k = 2): batched grid, then SciPy SLSQP on
     single evaluations exactly like the reference (likeli_optimizer.py:37-48).  The optimum sits at
