@@ -593,7 +593,10 @@ from sm_b200 import workloads
 X3, y3 = workloads.c3_lhs1024(n=600, k=8)
 e, p = workloads.c3_candidates(40, 8)
 b = Kriging(X3, y3).likelihood_batch(e, p)
-print(json.dumps(dict(b=[float(v) for v in b])))
+X4, y4 = workloads.c3_lhs1024(n=160, k=3)          # 3000 candidates: every CTA loops over several candidates
+e4, p4 = workloads.c3_candidates(3000, 3)
+c = Kriging(X4, y4).likelihood_batch(e4, p4)
+print(json.dumps(dict(b=[float(v) for v in b], c=[float(v) if np.isfinite(v) else None for v in c])))
 '''
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = {}
@@ -603,6 +606,12 @@ print(json.dumps(dict(b=[float(v) for v in b])))
         assert r.returncode == 0, r.stderr[-2000:]
         out[flag] = json.loads(r.stdout.strip().split('\n')[-1])
     assert np.max(rel(np.array(out['0']['b']), np.array(out['1']['b']))) < 1e-10   # cond ~1e4
+    c0 = np.array([np.nan if v is None else v for v in out['0']['c']])
+    c1 = np.array([np.nan if v is None else v for v in out['1']['c']])
+    assert np.array_equal(np.isfinite(c0), np.isfinite(c1)) and np.isfinite(c0).sum() > 2900
+    m = np.isfinite(c0)
+    d = rel(c0[m], c1[m])                         # log10 theta ~ U(-3, 1): the tail is ill-conditioned (cond up to ~1e10)
+    assert np.median(d) < 1e-11 and np.max(d) < 1e-6
 
 
 def test_lazy_objective_large_n(K):
