@@ -119,11 +119,11 @@ int sm_krig_nll_grid(const double* X, const double* y, int n, int k, const doubl
     a.C = c_count; a.c_begin = c_begin;
     a.theta_axis = theta_axis; a.T = T; a.P = P; a.dtab = dtab.as<double>();
     a.nll_out = nll_out;
-    // n <= 64, k <= 4: product-form entry tables (see egrid_kernel).  The choice depends on the problem shape
+    // n <= 96, k <= 4 (the warp-per-candidate kernel): product-form entry tables (see egrid_kernel).  The choice depends on the problem shape
     // only, never on the candidate range, so shards of one grid are bit-identical to the full evaluation.
     DevBuf egrid(st);
     const size_t egrid_bytes = (size_t)npad * npad * k * P * T * 8;
-    if (npad <= 64 && k <= 4 && egrid_bytes <= ((size_t)256 << 20)) {
+    if (npad <= 96 && k <= 4 && egrid_bytes <= ((size_t)256 << 20)) {
         SM_TRY(egrid.alloc(egrid_bytes));
         SM_TRY(launch_egrid(dtab.as<double>(), theta_axis, k, P, T, npad, egrid.as<double>(), st));
         L.n += 1;

@@ -178,12 +178,12 @@ __device__ __forceinline__ bool diag_factor(double c0, double c1, double* __rest
 // 19 slots instead of 28 at NTM = 8 -> 11.9 KB instead of 15.9 KB per candidate -> 16 resident warps per SM (the
 // register limit) instead of 14.  The map is a compile-time table; a map for NTM is valid for every NT <= NTM.
 struct SlotMap {
-    unsigned char s[8][8];
+    unsigned char s[12][12];
     int nslots;
 };
 __host__ __device__ constexpr SlotMap make_slot_map(int ntm) {
     SlotMap m{};
-    bool used[32] = {};
+    bool used[80] = {};
     int maxs = 0;
     for (int J = 0; J + 1 < ntm; ++J) {
         if (J >= 1)
@@ -199,13 +199,16 @@ __host__ __device__ constexpr SlotMap make_slot_map(int ntm) {
     m.nslots = maxs > 0 ? maxs : 1;
     return m;
 }
-__constant__ SlotMap c_slot_map8 = make_slot_map(8);  // every NTM <= 8 uses the NTM = 8 map (valid for NT <= 8)
+__constant__ SlotMap c_slot_map8 = make_slot_map(8);    // every NTM <= 8 uses the NTM = 8 map (valid for NT <= 8)
+__constant__ SlotMap c_slot_map12 = make_slot_map(12);  // NTM = 12 (64 < n <= 96): 41 slots, 23.5 KB per candidate
+__host__ __device__ constexpr int small_slots(int ntm) { return make_slot_map(ntm > 8 ? 12 : 8).nslots; }
 
 // shared memory per warp (doubles): tile slots | rhs rows (2 x npad) | W tile | diagonal working tile
-__host__ __device__ inline int small_warp_doubles(int ntm) { return make_slot_map(8).nslots * 64 + ntm * 16 + 128; }
+__host__ __device__ inline int small_warp_doubles(int ntm) { return small_slots(ntm) * 64 + ntm * 16 + 128; }
 
+// NTM <= 8: 16 warps per SM (128 registers); NTM = 12: shared memory allows 9 warps per SM, so up to 224 registers
 template <int NTM, int KD, int MODE>
-__global__ void __launch_bounds__(256, 2) krig_nll_small_kernel(const NllArgs a) {
+__global__ void __launch_bounds__(NTM > 8 ? 96 : 256, NTM > 8 ? 3 : 2) krig_nll_small_kernel(const NllArgs a) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int r = lane >> 2, q = lane & 3;
@@ -213,8 +216,9 @@ __global__ void __launch_bounds__(256, 2) krig_nll_small_kernel(const NllArgs a)
     double* etab = smem;                 // [32]
     double* y_s = etab + EXP_TAB;        // [8 NTM]
     double* mine = y_s + 8 * NTM + (size_t)wid * small_warp_doubles(NTM);
-    double* tiles = mine;                                   // tile (I, K), K < I, in slot c_slot_map8.s[I][K]
-    double* rhs_s = tiles + make_slot_map(8).nslots * 64;   // [Jt][2][8]: rows y^T / 1^T
+    double* tiles = mine;                                   // tile (I, K), K < I, in slot SM.s[I][K] (c_slot_map8 / c_slot_map12)
+    double* rhs_s = tiles + small_slots(NTM) * 64;          // [Jt][2][8]: rows y^T / 1^T
+    const SlotMap& SM = (NTM > 8) ? c_slot_map12 : c_slot_map8;
     double* wscr = rhs_s + NTM * 16;                        // [64] W_J in operand order
     double* dscr = wscr + 64;                               // [64] diagonal tile, column-major working copy
     const LaneOff lo(lane);
@@ -286,7 +290,7 @@ __global__ void __launch_bounds__(256, 2) krig_nll_small_kernel(const NllArgs a)
                     }
                     for (int K = 0; K < J; ++K) {
                         // operands first (independent LDS), then every first k-half, then every second k-half
-                        const double2 b = ld_frag_sw(tiles + c_slot_map8.s[J][K] * 64, lo);
+                        const double2 b = ld_frag_sw(tiles + SM.s[J][K] * 64, lo);
                         double2 av[4];
 #pragma unroll
                         for (int gg = 0; gg < 4; ++gg) {
@@ -294,7 +298,7 @@ __global__ void __launch_bounds__(256, 2) krig_nll_small_kernel(const NllArgs a)
                             av[gg] = b;  // g == 0: the diagonal tile, L_JK L_JK^T
                             if (g > 0 && g < NTM && g < cnt) {
                                 const int I = J + g;
-                                av[gg] = ld_frag_sw(tiles + c_slot_map8.s[I][K] * 64, lo);
+                                av[gg] = ld_frag_sw(tiles + SM.s[I][K] * 64, lo);
                             }
                         }
                         double a0 = 0.0, a1 = 0.0;
@@ -343,7 +347,7 @@ __global__ void __launch_bounds__(256, 2) krig_nll_small_kernel(const NllArgs a)
                             dc1 = acc[0][1];
                         } else if (g < NTM && g < cnt) {
                             const int I = J + g;
-                            st_acc_sw(tiles + c_slot_map8.s[I][J] * 64, lo, acc[gg][0], acc[gg][1]);
+                            st_acc_sw(tiles + SM.s[I][J] * 64, lo, acc[gg][0], acc[gg][1]);
                         }
                     }
                 }
@@ -377,7 +381,7 @@ __global__ void __launch_bounds__(256, 2) krig_nll_small_kernel(const NllArgs a)
                         t[gg][0] = t[gg][1] = 0.0;
                         if (g > 0 && g < NTM && g < cnt) {
                             const int I = J + g;
-                            pv[gg] = ld_frag_sw(tiles + c_slot_map8.s[I][J] * 64, lo);
+                            pv[gg] = ld_frag_sw(tiles + SM.s[I][J] * 64, lo);
                         }
                     }
                     double ra0 = 0.0, ra1 = 0.0;
@@ -399,7 +403,7 @@ __global__ void __launch_bounds__(256, 2) krig_nll_small_kernel(const NllArgs a)
                         const int g = g0 + gg;
                         if (g > 0 && g < NTM && g < cnt) {
                             const int I = J + g;
-                            st_acc_sw(tiles + c_slot_map8.s[I][J] * 64, lo, t[gg][0], t[gg][1]);
+                            st_acc_sw(tiles + SM.s[I][J] * 64, lo, t[gg][0], t[gg][1]);
                         }
                     }
                     if (g0 == 0 && r < 2) {
@@ -444,19 +448,19 @@ static cudaError_t launch_small_t(const NllArgs& a, int mode, cudaStream_t st) {
     const size_t per_sm = 228 * 1024, reserved = 1024;
     const size_t fixed = (EXP_TAB + 8 * NTM) * 8, per_warp = (size_t)small_warp_doubles(NTM) * 8;
     int best_w = 0, best_wpc = 1;
-    const int wpc_max = 8;
+    const int wpc_max = NTM > 8 ? 3 : 8, warp_cap = NTM > 8 ? 9 : 16;  // what the kernel's launch bounds allow
     for (int wpc = 1; wpc <= wpc_max; ++wpc) {  // warps (candidates) per CTA maximising resident warps per SM
         const size_t sm = fixed + wpc * per_warp;
         if (sm > smem_optin()) break;
         int ctas = (int)(per_sm / (sm + reserved));
         if (ctas > 32) ctas = 32;
         int w = ctas * wpc;
-        if (w > 16) w = 16;  // register file: 16 warps x 128 registers
+        if (w > warp_cap) w = warp_cap;  // register file
         if (w > best_w) { best_w = w; best_wpc = wpc; }
     }
     const size_t smem = fixed + best_wpc * per_warp;
     int ctas_per_sm = (int)(per_sm / (smem + reserved));
-    if (ctas_per_sm * best_wpc > 16) ctas_per_sm = 16 / best_wpc;
+    if (ctas_per_sm * best_wpc > warp_cap) ctas_per_sm = warp_cap / best_wpc;
     long long grid = (long long)sm_count() * ctas_per_sm;
     const long long need = (a.C + best_wpc - 1) / best_wpc;
     if (grid > need) grid = need;
@@ -492,15 +496,16 @@ static cudaError_t launch_small_k(const NllArgs& a, int mode, cudaStream_t st) {
     }
 }
 
-// n <= 64 and k <= 4: the specialised kernel; anything else returns cudaErrorNotSupported and the caller
+// n <= 96 and k <= 4: the specialised kernel; anything else returns cudaErrorNotSupported and the caller
 // uses the generic engine
 cudaError_t launch_nll_small(const NllArgs& a, int mode, cudaStream_t st) {
     const int NT = a.npad / 8;
-    if (a.k > 4 || NT > 8 || a.C <= 0) return cudaErrorNotSupported;
+    if (a.k > 4 || NT > 12 || a.C <= 0) return cudaErrorNotSupported;
     if (NT <= 2) return launch_small_k<2>(a, mode, st);
     if (NT <= 4) return launch_small_k<4>(a, mode, st);
     if (NT <= 6) return launch_small_k<6>(a, mode, st);
-    return launch_small_k<8>(a, mode, st);
+    if (NT <= 8) return launch_small_k<8>(a, mode, st);
+    return launch_small_k<12>(a, mode, st);  // 64 < n <= 96: 9 warps per SM
 }
 
 }  // namespace smb
