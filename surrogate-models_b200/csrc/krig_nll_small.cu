@@ -178,7 +178,7 @@ __device__ __forceinline__ bool diag_factor(double c0, double c1, double* __rest
 // 19 slots instead of 28 at NTM = 8 -> 11.9 KB instead of 15.9 KB per candidate -> 16 resident warps per SM (the
 // register limit) instead of 14.  The map is a compile-time table; a map for NTM is valid for every NT <= NTM.
 struct SlotMap {
-    unsigned char s[12][12];
+    unsigned char s[16][16];
     int nslots;
 };
 __host__ __device__ constexpr SlotMap make_slot_map(int ntm) {
@@ -201,14 +201,15 @@ __host__ __device__ constexpr SlotMap make_slot_map(int ntm) {
 }
 __constant__ SlotMap c_slot_map8 = make_slot_map(8);    // every NTM <= 8 uses the NTM = 8 map (valid for NT <= 8)
 __constant__ SlotMap c_slot_map12 = make_slot_map(12);  // NTM = 12 (64 < n <= 96): 41 slots, 23.5 KB per candidate
-__host__ __device__ constexpr int small_slots(int ntm) { return make_slot_map(ntm > 8 ? 12 : 8).nslots; }
+__constant__ SlotMap c_slot_map16 = make_slot_map(16);  // NTM = 16 (96 < n <= 128): 71 slots, 38.5 KB per candidate
+__host__ __device__ constexpr int small_slots(int ntm) { return make_slot_map(ntm > 12 ? 16 : (ntm > 8 ? 12 : 8)).nslots; }
 
 // shared memory per warp (doubles): tile slots | rhs rows (2 x npad) | W tile | diagonal working tile
 __host__ __device__ inline int small_warp_doubles(int ntm) { return small_slots(ntm) * 64 + ntm * 16 + 128; }
 
-// NTM <= 8: 16 warps per SM (128 registers); NTM = 12: shared memory allows 9 warps per SM, so up to 224 registers
+// NTM <= 8: 16 warps per SM (128 registers); NTM = 12 / 16: shared memory allows 9 / 5 warps per SM, so more registers
 template <int NTM, int KD, int MODE>
-__global__ void __launch_bounds__(NTM > 8 ? 96 : 256, NTM > 8 ? 3 : 2) krig_nll_small_kernel(const NllArgs a) {
+__global__ void __launch_bounds__(NTM > 12 ? 32 : (NTM > 8 ? 96 : 256), NTM > 12 ? 5 : (NTM > 8 ? 3 : 2)) krig_nll_small_kernel(const NllArgs a) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int r = lane >> 2, q = lane & 3;
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(NTM > 8 ? 96 : 256, NTM > 8 ? 3 : 2) krig_nll_
     double* mine = y_s + 8 * NTM + (size_t)wid * small_warp_doubles(NTM);
     double* tiles = mine;                                   // tile (I, K), K < I, in slot SM.s[I][K] (c_slot_map8 / c_slot_map12)
     double* rhs_s = tiles + small_slots(NTM) * 64;          // [Jt][2][8]: rows y^T / 1^T
-    const SlotMap& SM = (NTM > 8) ? c_slot_map12 : c_slot_map8;
+    const SlotMap& SM = (NTM > 12) ? c_slot_map16 : ((NTM > 8) ? c_slot_map12 : c_slot_map8);
     double* wscr = rhs_s + NTM * 16;                        // [64] W_J in operand order
     double* dscr = wscr + 64;                               // [64] diagonal tile, column-major working copy
     const LaneOff lo(lane);
@@ -448,7 +449,7 @@ static cudaError_t launch_small_t(const NllArgs& a, int mode, cudaStream_t st) {
     const size_t per_sm = 228 * 1024, reserved = 1024;
     const size_t fixed = (EXP_TAB + 8 * NTM) * 8, per_warp = (size_t)small_warp_doubles(NTM) * 8;
     int best_w = 0, best_wpc = 1;
-    const int wpc_max = NTM > 8 ? 3 : 8, warp_cap = NTM > 8 ? 9 : 16;  // what the kernel's launch bounds allow
+    const int wpc_max = NTM > 12 ? 1 : (NTM > 8 ? 3 : 8), warp_cap = NTM > 12 ? 5 : (NTM > 8 ? 9 : 16);  // launch bounds
     for (int wpc = 1; wpc <= wpc_max; ++wpc) {  // warps (candidates) per CTA maximising resident warps per SM
         const size_t sm = fixed + wpc * per_warp;
         if (sm > smem_optin()) break;
@@ -496,16 +497,17 @@ static cudaError_t launch_small_k(const NllArgs& a, int mode, cudaStream_t st) {
     }
 }
 
-// n <= 96 and k <= 4: the specialised kernel; anything else returns cudaErrorNotSupported and the caller
+// n <= 128 and k <= 4: the specialised kernel; anything else returns cudaErrorNotSupported and the caller
 // uses the generic engine
 cudaError_t launch_nll_small(const NllArgs& a, int mode, cudaStream_t st) {
     const int NT = a.npad / 8;
-    if (a.k > 4 || NT > 12 || a.C <= 0) return cudaErrorNotSupported;
+    if (a.k > 4 || NT > 16 || a.C <= 0) return cudaErrorNotSupported;
     if (NT <= 2) return launch_small_k<2>(a, mode, st);
     if (NT <= 4) return launch_small_k<4>(a, mode, st);
     if (NT <= 6) return launch_small_k<6>(a, mode, st);
     if (NT <= 8) return launch_small_k<8>(a, mode, st);
-    return launch_small_k<12>(a, mode, st);  // 64 < n <= 96: 9 warps per SM
+    if (NT <= 12) return launch_small_k<12>(a, mode, st);  // 64 < n <= 96: 9 warps per SM
+    return launch_small_k<16>(a, mode, st);                 // 96 < n <= 128: 5 warps per SM
 }
 
 }  // namespace smb
