@@ -209,7 +209,9 @@ __host__ __device__ inline int small_warp_doubles(int ntm) { return small_slots(
 
 // NTM <= 8: 16 warps per SM (128 registers); NTM = 12 / 16: shared memory allows 9 / 5 warps per SM, so more registers
 template <int NTM, int KD, int MODE>
-__global__ void __launch_bounds__(NTM > 12 ? 32 : (NTM > 8 ? 96 : 256), NTM > 12 ? 5 : (NTM > 8 ? 3 : 2)) krig_nll_small_kernel(const NllArgs a) {
+// KD = 8 (k = 5..8) keeps 8 table pointers / weights / exponents per thread: 8 warps per SM, up to 255 registers
+__global__ void __launch_bounds__(KD > 4 ? 32 : (NTM > 12 ? 32 : (NTM > 8 ? 96 : 256)), KD > 4 ? (NTM > 12 ? 5 : 8) : (NTM > 12 ? 5 : (NTM > 8 ? 3 : 2)))
+krig_nll_small_kernel(const NllArgs a) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int r = lane >> 2, q = lane & 3;
@@ -237,27 +239,32 @@ __global__ void __launch_bounds__(NTM > 12 ? 32 : (NTM > 8 ? 96 : 256), NTM > 12
         if (MODE == 0 || MODE == 2) {
             long long tk = 1;
 #pragma unroll
-            for (int d = 0; d < KD; ++d) tk *= a.T;
+            for (int d = 0; d < KD; ++d)
+                if (d < a.k) tk *= a.T;
             const long long cg = a.c_begin + c;
             long long it = cg % tk, ip = cg / tk;
 #pragma unroll
             for (int d = 0; d < KD; ++d) {
+                const int dd = (d < a.k) ? d : a.k - 1;  // KD > k (the KD = 8 instantiation for k = 5..7): weight 0
                 if (MODE == 0) {
-                    P.th[d] = a.theta_axis[it % a.T];
-                    P.tab[d] = a.dtab + ((long long)d * a.P + (ip % a.P)) * per;
+                    P.th[d] = (d < a.k) ? a.theta_axis[it % a.T] : 0.0;
+                    P.tab[d] = a.dtab + ((long long)dd * a.P + (ip % a.P)) * per;
                 } else {
                     P.th[d] = 0.0;
-                    P.tab[d] = a.egrid + (((long long)d * a.P + (ip % a.P)) * a.T + (it % a.T)) * per;
+                    P.tab[d] = a.egrid + (((long long)dd * a.P + (ip % a.P)) * a.T + (it % a.T)) * per;
                 }
-                it /= a.T;
-                ip /= a.P;
+                if (d + 1 < a.k) {
+                    it /= a.T;
+                    ip /= a.P;
+                }
             }
         } else {
 #pragma unroll
             for (int d = 0; d < KD; ++d) {
-                P.th[d] = a.theta[c * KD + d];
-                P.pw[d] = a.p[c * KD + d];
-                P.tab[d] = a.logtab + d * per;
+                const int dd = (d < a.k) ? d : a.k - 1;
+                P.th[d] = (d < a.k) ? a.theta[c * a.k + dd] : 0.0;
+                P.pw[d] = a.p[c * a.k + dd];
+                P.tab[d] = a.logtab + dd * per;
             }
         }
         double prod = 1.0;
@@ -449,7 +456,8 @@ static cudaError_t launch_small_t(const NllArgs& a, int mode, cudaStream_t st) {
     const size_t per_sm = 228 * 1024, reserved = 1024;
     const size_t fixed = (EXP_TAB + 8 * NTM) * 8, per_warp = (size_t)small_warp_doubles(NTM) * 8;
     int best_w = 0, best_wpc = 1;
-    const int wpc_max = NTM > 12 ? 1 : (NTM > 8 ? 3 : 8), warp_cap = NTM > 12 ? 5 : (NTM > 8 ? 9 : 16);  // launch bounds
+    const int wpc_max = (KD > 4 || NTM > 12) ? 1 : (NTM > 8 ? 3 : 8);                              // launch bounds
+    const int warp_cap = NTM > 12 ? 5 : (KD > 4 ? 8 : (NTM > 8 ? 9 : 16));
     for (int wpc = 1; wpc <= wpc_max; ++wpc) {  // warps (candidates) per CTA maximising resident warps per SM
         const size_t sm = fixed + wpc * per_warp;
         if (sm > smem_optin()) break;
@@ -493,6 +501,9 @@ static cudaError_t launch_small_k(const NllArgs& a, int mode, cudaStream_t st) {
         case 2: return launch_small_t<NTM, 2>(a, mode, st);
         case 3: return launch_small_t<NTM, 3>(a, mode, st);
         case 4: return launch_small_t<NTM, 4>(a, mode, st);
+        case 5: case 6: case 7: case 8:
+            if (mode == 0 && a.egrid) return cudaErrorNotSupported;  // product form is built for k <= 4 only
+            return launch_small_t<NTM, 8>(a, mode, st);
         default: return cudaErrorNotSupported;
     }
 }
@@ -501,7 +512,7 @@ static cudaError_t launch_small_k(const NllArgs& a, int mode, cudaStream_t st) {
 // uses the generic engine
 cudaError_t launch_nll_small(const NllArgs& a, int mode, cudaStream_t st) {
     const int NT = a.npad / 8;
-    if (a.k > 4 || NT > 16 || a.C <= 0) return cudaErrorNotSupported;
+    if (a.k > 8 || NT > 16 || a.C <= 0) return cudaErrorNotSupported;
     if (NT <= 2) return launch_small_k<2>(a, mode, st);
     if (NT <= 4) return launch_small_k<4>(a, mode, st);
     if (NT <= 6) return launch_small_k<6>(a, mode, st);

@@ -214,11 +214,11 @@ def test_c3_n1024_k8(gold, K):
     assert np.max(rel(yy, yr)) < 1e-8 and np.max(np.abs(mse - mr)) < 1e-8 * k._fit['sigma2']
 
 
-@pytest.mark.parametrize('n,k_', [(1, 1), (2, 1), (7, 2), (13, 3), (65, 2), (73, 2), (80, 5), (90, 4), (96, 3), (97, 2), (104, 2), (128, 4), (129, 4), (144, 2),
+@pytest.mark.parametrize('n,k_', [(1, 1), (2, 1), (7, 2), (13, 3), (30, 6), (64, 8), (65, 2), (73, 2), (80, 5), (100, 7), (90, 4), (96, 3), (97, 2), (104, 2), (128, 4), (129, 4), (144, 2),
                                   (225, 3), (230, 16)])
 def test_ragged_sizes_against_oracle(K, n, k_):
-    """sizes straddling every kernel variant / padding boundary (8-tiles; n <= 128 and k <= 4 warp-per-candidate,
-    n <= 128 with k > 4: CTA in shared memory, <= 144 macro-panel kernel, beyond: dataflow kernel)"""
+    """sizes straddling every kernel variant / padding boundary (8-tiles; n <= 128 and k <= 8 warp-per-candidate,
+    n <= 128 with k > 8: CTA in shared memory, <= 144 macro-panel kernel, beyond: dataflow kernel)"""
     rng = np.random.default_rng(n * 100 + k_)
     X = rng.uniform(0, 10, (n, k_))
     y = np.sin(X.sum(axis=1)) + 0.1 * X[:, 0] ** 2

@@ -12,7 +12,7 @@ from mylibs.kriging import Kriging  # noqa: E402
 from sm_b200 import _cabi, device, workloads  # noqa: E402
 
 L = _cabi.lib()
-for n, k, C in [(64, 2, 100000), (72, 2, 50000), (96, 2, 50000), (96, 4, 50000), (104, 2, 20000), (128, 2, 20000), (144, 2, 20000)]:
+for n, k, C in [(64, 2, 100000), (64, 8, 50000), (36, 6, 100000), (96, 8, 20000), (128, 8, 20000), (96, 2, 50000), (128, 2, 20000)]:
     X, y = workloads.c3_lhs1024(n=n, k=k)
     e, p = workloads.c3_candidates(C, k)
     kr = Kriging(X * 10, y)
@@ -26,6 +26,10 @@ for n, k, C in [(64, 2, 100000), (72, 2, 50000), (96, 2, 50000), (96, 4, 50000),
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(); f(); b.record(); torch.cuda.synchronize()
     ms = a.elapsed_time(b)
+    fl = n ** 3 / 3 + (k + 2) * n ** 2
+    if k > 2:
+        print(f'n={n:4d} k={k}: list {C / ms * 1e3:.4g} evals/s {fl * C / ms / 1e9:.2f} TFLOP/s', flush=True)
+        continue
     T, P = 10, 5
     bv, bi, _ = kr.likelihood_grid(T, P)
     torch.cuda.synchronize()
