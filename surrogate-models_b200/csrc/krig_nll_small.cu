@@ -16,7 +16,7 @@
 
 namespace smb {
 
-#ifdef SMB_PHASE_TIMING
+#if defined(SMB_PHASE_TIMING) && !defined(SMB_SMALL_K8_TU)
 __device__ unsigned long long g_small_phase[8];
 #define SPH_BEGIN() long long _sp_t = clock64()
 #define SPH_MARK(slot)                                                                              \
@@ -199,9 +199,9 @@ __host__ __device__ constexpr SlotMap make_slot_map(int ntm) {
     m.nslots = maxs > 0 ? maxs : 1;
     return m;
 }
-__constant__ SlotMap c_slot_map8 = make_slot_map(8);    // every NTM <= 8 uses the NTM = 8 map (valid for NT <= 8)
-__constant__ SlotMap c_slot_map12 = make_slot_map(12);  // NTM = 12 (64 < n <= 96): 41 slots, 23.5 KB per candidate
-__constant__ SlotMap c_slot_map16 = make_slot_map(16);  // NTM = 16 (96 < n <= 128): 71 slots, 38.5 KB per candidate
+static __constant__ SlotMap c_slot_map8 = make_slot_map(8);    // every NTM <= 8 uses the NTM = 8 map (valid for NT <= 8)
+static __constant__ SlotMap c_slot_map12 = make_slot_map(12);  // NTM = 12 (64 < n <= 96): 41 slots, 23.5 KB per candidate
+static __constant__ SlotMap c_slot_map16 = make_slot_map(16);  // NTM = 16 (96 < n <= 128): 71 slots, 38.5 KB per candidate
 __host__ __device__ constexpr int small_slots(int ntm) { return make_slot_map(ntm > 12 ? 16 : (ntm > 8 ? 12 : 8)).nslots; }
 
 // shared memory per warp (doubles): tile slots | rhs rows (2 x npad) | W tile | diagonal working tile
@@ -475,10 +475,14 @@ static cudaError_t launch_small_t(const NllArgs& a, int mode, cudaStream_t st) {
     if (grid > need) grid = need;
     cudaError_t e;
     if (mode == 0 && a.egrid) {
-        e = cudaFuncSetAttribute(krig_nll_small_kernel<NTM, KD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        cudaFuncSetAttribute(krig_nll_small_kernel<NTM, KD, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        krig_nll_small_kernel<NTM, KD, 2><<<(int)grid, 32 * best_wpc, smem, st>>>(a);
+        if constexpr (KD <= 4) {  // the product-form tables exist for k <= 4 only
+            e = cudaFuncSetAttribute(krig_nll_small_kernel<NTM, KD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            cudaFuncSetAttribute(krig_nll_small_kernel<NTM, KD, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            krig_nll_small_kernel<NTM, KD, 2><<<(int)grid, 32 * best_wpc, smem, st>>>(a);
+        } else {
+            return cudaErrorNotSupported;
+        }
     } else if (mode == 0) {
         e = cudaFuncSetAttribute(krig_nll_small_kernel<NTM, KD, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -494,6 +498,20 @@ static cudaError_t launch_small_t(const NllArgs& a, int mode, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+// k = 5..8 (KD = 8) is compiled in its own translation unit (krig_nll_small8.cu includes this file with
+// SMB_SMALL_K8_TU defined) so the two halves of the instantiation matrix build in parallel
+cudaError_t launch_nll_small_k8(const NllArgs& a, int mode, cudaStream_t st);
+
+#ifdef SMB_SMALL_K8_TU
+cudaError_t launch_nll_small_k8(const NllArgs& a, int mode, cudaStream_t st) {
+    const int NT = a.npad / 8;
+    if (mode == 0 && a.egrid) return cudaErrorNotSupported;  // product form is built for k <= 4 only
+    if (NT <= 4) return launch_small_t<4, 8>(a, mode, st);
+    if (NT <= 8) return launch_small_t<8, 8>(a, mode, st);
+    if (NT <= 12) return launch_small_t<12, 8>(a, mode, st);
+    return launch_small_t<16, 8>(a, mode, st);
+}
+#else
 template <int NTM>
 static cudaError_t launch_small_k(const NllArgs& a, int mode, cudaStream_t st) {
     switch (a.k) {
@@ -501,18 +519,16 @@ static cudaError_t launch_small_k(const NllArgs& a, int mode, cudaStream_t st) {
         case 2: return launch_small_t<NTM, 2>(a, mode, st);
         case 3: return launch_small_t<NTM, 3>(a, mode, st);
         case 4: return launch_small_t<NTM, 4>(a, mode, st);
-        case 5: case 6: case 7: case 8:
-            if (mode == 0 && a.egrid) return cudaErrorNotSupported;  // product form is built for k <= 4 only
-            return launch_small_t<NTM, 8>(a, mode, st);
         default: return cudaErrorNotSupported;
     }
 }
 
-// n <= 128 and k <= 4: the specialised kernel; anything else returns cudaErrorNotSupported and the caller
+// n <= 128 and k <= 8: the specialised kernel; anything else returns cudaErrorNotSupported and the caller
 // uses the generic engine
 cudaError_t launch_nll_small(const NllArgs& a, int mode, cudaStream_t st) {
     const int NT = a.npad / 8;
     if (a.k > 8 || NT > 16 || a.C <= 0) return cudaErrorNotSupported;
+    if (a.k > 4) return launch_nll_small_k8(a, mode, st);
     if (NT <= 2) return launch_small_k<2>(a, mode, st);
     if (NT <= 4) return launch_small_k<4>(a, mode, st);
     if (NT <= 6) return launch_small_k<6>(a, mode, st);
@@ -520,5 +536,6 @@ cudaError_t launch_nll_small(const NllArgs& a, int mode, cudaStream_t st) {
     if (NT <= 12) return launch_small_k<12>(a, mode, st);  // 64 < n <= 96: 9 warps per SM
     return launch_small_k<16>(a, mode, st);                 // 96 < n <= 128: 5 warps per SM
 }
+#endif
 
 }  // namespace smb
