@@ -233,29 +233,69 @@ krig_nll_small_kernel(const NllArgs a) {
     const long long per = (long long)npad * npad;
     const long long first = (long long)blockIdx.x * nwarps + wid, stride = (long long)gridDim.x * nwarps;
 
+    // grid decode: T^k and P^k as 32-bit numbers when they fit
+    unsigned tk32 = 1;
+    bool fast_decode = (MODE != 1);
+    if (MODE != 1) {
+        unsigned long long tk = 1, pk = 1;
+        for (int d = 0; d < a.k; ++d) {
+            tk *= (unsigned long long)a.T;
+            pk *= (unsigned long long)a.P;
+            if (tk > 0xffffffffull || pk > 0xffffffffull) {
+                fast_decode = false;
+                tk = pk = 1;
+            }
+        }
+        tk32 = (unsigned)tk;
+    }
+
     for (long long c = first; c < a.C; c += stride) {
         // ---------------------------------------------------------------- candidate parameters
         SmallParams<KD> P;
         if (MODE == 0 || MODE == 2) {
-            long long tk = 1;
-#pragma unroll
-            for (int d = 0; d < KD; ++d)
-                if (d < a.k) tk *= a.T;
+            // flat index -> per-dimension digits (dimension 0 the fastest).  32-bit arithmetic whenever the index and
+            // the digit spaces fit (always, for k <= 4 grids): the 64-bit divisions of the first version were 2 500 of
+            // the 7 500 instructions per candidate (ncu source page, capture h)
             const long long cg = a.c_begin + c;
-            long long it = cg % tk, ip = cg / tk;
+            unsigned dt[KD], dp[KD];
+            if (fast_decode && cg < 0xffffffffll) {
+                const unsigned cu = (unsigned)cg;
+                unsigned ip = cu / tk32, it = cu - ip * tk32;
+#pragma unroll
+                for (int d = 0; d < KD; ++d) {
+                    const unsigned qt = it / (unsigned)a.T, qp = ip / (unsigned)a.P;
+                    dt[d] = it - qt * (unsigned)a.T;
+                    dp[d] = ip - qp * (unsigned)a.P;
+                    if (d + 1 < a.k) {
+                        it = qt;
+                        ip = qp;
+                    }
+                }
+            } else {
+                long long tk = 1;
+#pragma unroll
+                for (int d = 0; d < KD; ++d)
+                    if (d < a.k) tk *= a.T;
+                long long it = cg % tk, ip = cg / tk;
+#pragma unroll
+                for (int d = 0; d < KD; ++d) {
+                    dt[d] = (unsigned)(it % a.T);
+                    dp[d] = (unsigned)(ip % a.P);
+                    if (d + 1 < a.k) {
+                        it /= a.T;
+                        ip /= a.P;
+                    }
+                }
+            }
 #pragma unroll
             for (int d = 0; d < KD; ++d) {
                 const int dd = (d < a.k) ? d : a.k - 1;  // KD > k (the KD = 8 instantiation for k = 5..7): weight 0
                 if (MODE == 0) {
-                    P.th[d] = (d < a.k) ? a.theta_axis[it % a.T] : 0.0;
-                    P.tab[d] = a.dtab + ((long long)dd * a.P + (ip % a.P)) * per;
+                    P.th[d] = (d < a.k) ? a.theta_axis[dt[d]] : 0.0;
+                    P.tab[d] = a.dtab + ((long long)dd * a.P + dp[d]) * per;
                 } else {
                     P.th[d] = 0.0;
-                    P.tab[d] = a.egrid + (((long long)dd * a.P + (ip % a.P)) * a.T + (it % a.T)) * per;
-                }
-                if (d + 1 < a.k) {
-                    it /= a.T;
-                    ip /= a.P;
+                    P.tab[d] = a.egrid + (((long long)dd * a.P + dp[d]) * a.T + dt[d]) * per;
                 }
             }
         } else {
