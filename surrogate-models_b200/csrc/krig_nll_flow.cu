@@ -88,7 +88,9 @@ __device__ __forceinline__ void fcp_async16(void* smem_dst, const void* gmem_src
 }
 __device__ __forceinline__ void fcp_async16(void* smem_dst, const void* gmem_src) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
+    // B strips: also cached in L1 -- the warps of a CTA read the same strip within a short window (+3 %, measured);
+    // same-SM stores keep L1 coherent, and every workspace belongs to one CTA
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void fcp_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>

@@ -101,12 +101,12 @@ def main():
     quick = '--quick' in sys.argv
     parity = [(136, 2, 8), (200, 3, 8), (256, 8, 8), (300, 8, 8), (520, 4, 8), (1024, 8, 6)]
     grid = [(200, 2, 3, 2)]
-    timing = [(256, 8, 9472), (512, 8, 2368), (1024, 8, 1184), (1536, 8, 592), (2048, 8, 296)]
+    timing = [(256, 8, 9472), (512, 8, 2368), (1024, 8, 1184), (2048, 8, 296)]
     if quick:
         timing = [(256, 8, 2368), (512, 8, 1184), (1024, 8, 592)]
     configs = []
 
-    for cfg in ('42', '43', '63', '73'):
+    for cfg in ('42', '63'):
         configs.append((f'flow cfg {cfg}', {'SMB_FLOW_CFG': cfg, 'SMB_FLOW_MIN_NT': '16'}, False))
 
     for name, env, with_parity in configs:
