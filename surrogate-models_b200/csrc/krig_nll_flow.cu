@@ -96,9 +96,12 @@ __device__ __forceinline__ void fcp_commit() { asm volatile("cp.async.commit_gro
 template <int N>
 __device__ __forceinline__ void fcp_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+#ifndef FLOW_SLEEP_NS
+#define FLOW_SLEEP_NS 100
+#endif
 __device__ __forceinline__ void wait_ge(const int* p, int v) {
     const volatile int* vp = p;
-    while (*vp < v) __nanosleep(100);
+    while (*vp < v) __nanosleep(FLOW_SLEEP_NS);
     __threadfence_block();
 }
 
@@ -741,11 +744,20 @@ static cudaError_t launch_flow_t(NllArgs a, int mode, cudaStream_t st) {
     auto kern = (mode == 0) ? krig_nll_flow_kernel<LW, ST, 0, CPS> : krig_nll_flow_kernel<LW, ST, 1, CPS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    // carve out what CPS resident CTAs need (static + dynamic + 1 KB reserved each) and leave the rest to L1, which
+    // serves the B strips
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess) return e;
+    const size_t need = (size_t)CPS * (smem + fa.sharedSizeBytes + 1024);
+    int pct = (int)((need * 100 + 228 * 1024 - 1) / (228 * 1024));
+    if (pct > 100) pct = 100;
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
     int per_sm = 1;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, LW * 32, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
+    if (per_sm > CPS) per_sm = CPS;
     long long grid = (long long)sm_count() * per_sm;
     if (grid > a.C) grid = a.C;
     const long long ws_cap = (long long)(((size_t)24 << 30) / tile_bytes);
