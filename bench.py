@@ -359,10 +359,22 @@ def run_gpu(args):
         t_bound3 = C3 * (flops_like(n3, 8) / (peak_tf * 1e12) + 9 * n3 * (n3 - 1) / 2 / (exp_gops * 1e9))
         return {'n': n3, 'k': 8, 'value': world * C3 / (ms3 * 1e-3), 'unit': 'evals/s', 'candidates_per_gpu': C3, 'ms': ms3,
                 'tflops_fma_only': tf, 'frac_of_fp64_peak': tf / peak_tf, 'frac_two_resource': t_bound3 / (ms3 * 1e-3)}
+    def large_n_grid_point(n3, k3, T3, P3):
+        """grid mode at large n: the candidates share |dx|^p tables, so no per-candidate powers -- the Cholesky part alone"""
+        X3, y3 = workloads.c3_lhs1024(n=n3, k=k3)
+        kg = Kriging(X3 * 10, y3)
+        C3 = (T3 ** k3) * (P3 ** k3)
+        ms3 = timed_ms(lambda: kg.likelihood_grid(T3, P3, return_nll=False))
+        _, _, nllg = kg.likelihood_grid(T3, P3, return_nll=True)
+        tf = flops_like(n3, k3) * C3 / (ms3 * 1e-3) / 1e12
+        return {'n': n3, 'k': k3, 'mode': f'grid {T3}^{k3} x {P3}^{k3}', 'value': world * C3 / (ms3 * 1e-3), 'unit': 'evals/s',
+                'candidates_per_gpu': C3, 'ms': ms3, 'tflops_fma_only': tf, 'frac_of_fp64_peak': tf / peak_tf,
+                'finite_fraction': float(np.isfinite(nllg.cpu().numpy()).mean())}
     c3pt = large_n_point(1024, 1184)
     secondary_c3 = dict(c3pt, metric='kriging likelihood evaluations/s (n=1024, k=8, list mode)',
                         kernel='krig_nll_flow_kernel<6,3,1,2> (n > 352: dataflow kernel; 128 < n <= 352: krig_nll_large_kernel)',
-                        other_sizes=[large_n_point(512, 2368), large_n_point(2048, 296)])
+                        other_sizes=[large_n_point(512, 2368), large_n_point(2048, 296)],
+                        grid_mode=large_n_grid_point(1024, 3, 8, 3))
     # C4: gaussian RBF, n = 4096: weight solve + evaluation at 2e6 points per GPU
     from mylibs.rbf import RBF
     X4, y4 = workloads.c4_rbf4096()
