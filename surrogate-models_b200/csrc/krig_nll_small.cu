@@ -178,12 +178,12 @@ __device__ __forceinline__ bool diag_factor(double c0, double c1, double* __rest
 // 19 slots instead of 28 at NTM = 8 -> 11.9 KB instead of 15.9 KB per candidate -> 16 resident warps per SM (the
 // register limit) instead of 14.  The map is a compile-time table; a map for NTM is valid for every NT <= NTM.
 struct SlotMap {
-    unsigned char s[16][16];
+    unsigned char s[18][18];
     int nslots;
 };
 __host__ __device__ constexpr SlotMap make_slot_map(int ntm) {
     SlotMap m{};
-    bool used[80] = {};
+    bool used[128] = {};
     int maxs = 0;
     for (int J = 0; J + 1 < ntm; ++J) {
         if (J >= 1)
@@ -202,7 +202,8 @@ __host__ __device__ constexpr SlotMap make_slot_map(int ntm) {
 static __constant__ SlotMap c_slot_map8 = make_slot_map(8);    // every NTM <= 8 uses the NTM = 8 map (valid for NT <= 8)
 static __constant__ SlotMap c_slot_map12 = make_slot_map(12);  // NTM = 12 (64 < n <= 96): 41 slots, 23.5 KB per candidate
 static __constant__ SlotMap c_slot_map16 = make_slot_map(16);  // NTM = 16 (96 < n <= 128): 71 slots, 38.5 KB per candidate
-__host__ __device__ constexpr int small_slots(int ntm) { return make_slot_map(ntm > 12 ? 16 : (ntm > 8 ? 12 : 8)).nslots; }
+static __constant__ SlotMap c_slot_map18 = make_slot_map(18);  // NTM = 18 (128 < n <= 144): 89 slots, 48 KB per candidate
+__host__ __device__ constexpr int small_slots(int ntm) { return make_slot_map(ntm > 16 ? 18 : (ntm > 12 ? 16 : (ntm > 8 ? 12 : 8))).nslots; }
 
 // shared memory per warp (doubles): tile slots | rhs rows (2 x npad) | W tile | diagonal working tile
 __host__ __device__ inline int small_warp_doubles(int ntm) { return small_slots(ntm) * 64 + ntm * 16 + 128; }
@@ -210,7 +211,8 @@ __host__ __device__ inline int small_warp_doubles(int ntm) { return small_slots(
 // NTM <= 8: 16 warps per SM (128 registers); NTM = 12 / 16: shared memory allows 9 / 5 warps per SM, so more registers
 template <int NTM, int KD, int MODE>
 // KD = 8 (k = 5..8) keeps 8 table pointers / weights / exponents per thread: 8 warps per SM, up to 255 registers
-__global__ void __launch_bounds__(KD > 4 ? 32 : (NTM > 12 ? 32 : (NTM > 8 ? 96 : 256)), KD > 4 ? (NTM > 12 ? 5 : 8) : (NTM > 12 ? 5 : (NTM > 8 ? 3 : 2)))
+__global__ void __launch_bounds__(KD > 4 ? 32 : (NTM > 12 ? 32 : (NTM > 8 ? 96 : 256)),
+                                  NTM > 16 ? 4 : (KD > 4 ? (NTM > 12 ? 5 : 8) : (NTM > 12 ? 5 : (NTM > 8 ? 3 : 2))))
 krig_nll_small_kernel(const NllArgs a) {
     extern __shared__ __align__(16) double smem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -221,7 +223,7 @@ krig_nll_small_kernel(const NllArgs a) {
     double* mine = y_s + 8 * NTM + (size_t)wid * small_warp_doubles(NTM);
     double* tiles = mine;                                   // tile (I, K), K < I, in slot SM.s[I][K] (c_slot_map8 / c_slot_map12)
     double* rhs_s = tiles + small_slots(NTM) * 64;          // [Jt][2][8]: rows y^T / 1^T
-    const SlotMap& SM = (NTM > 12) ? c_slot_map16 : ((NTM > 8) ? c_slot_map12 : c_slot_map8);
+    const SlotMap& SM = (NTM > 16) ? c_slot_map18 : ((NTM > 12) ? c_slot_map16 : ((NTM > 8) ? c_slot_map12 : c_slot_map8));
     double* wscr = rhs_s + NTM * 16;                        // [64] W_J in operand order
     double* dscr = wscr + 64;                               // [64] diagonal tile, column-major working copy
     const LaneOff lo(lane);
@@ -497,7 +499,7 @@ static cudaError_t launch_small_t(const NllArgs& a, int mode, cudaStream_t st) {
     const size_t fixed = (EXP_TAB + 8 * NTM) * 8, per_warp = (size_t)small_warp_doubles(NTM) * 8;
     int best_w = 0, best_wpc = 1;
     const int wpc_max = (KD > 4 || NTM > 12) ? 1 : (NTM > 8 ? 3 : 8);                              // launch bounds
-    const int warp_cap = NTM > 12 ? 5 : (KD > 4 ? 8 : (NTM > 8 ? 9 : 16));
+    const int warp_cap = NTM > 16 ? 4 : (NTM > 12 ? 5 : (KD > 4 ? 8 : (NTM > 8 ? 9 : 16)));
     for (int wpc = 1; wpc <= wpc_max; ++wpc) {  // warps (candidates) per CTA maximising resident warps per SM
         const size_t sm = fixed + wpc * per_warp;
         if (sm > smem_optin()) break;
@@ -549,7 +551,8 @@ cudaError_t launch_nll_small_k8(const NllArgs& a, int mode, cudaStream_t st) {
     if (NT <= 4) return launch_small_t<4, 8>(a, mode, st);
     if (NT <= 8) return launch_small_t<8, 8>(a, mode, st);
     if (NT <= 12) return launch_small_t<12, 8>(a, mode, st);
-    return launch_small_t<16, 8>(a, mode, st);
+    if (NT <= 16) return launch_small_t<16, 8>(a, mode, st);
+    return launch_small_t<18, 8>(a, mode, st);
 }
 #else
 template <int NTM>
@@ -563,18 +566,19 @@ static cudaError_t launch_small_k(const NllArgs& a, int mode, cudaStream_t st) {
     }
 }
 
-// n <= 128 and k <= 8: the specialised kernel; anything else returns cudaErrorNotSupported and the caller
+// n <= 144 and k <= 8: the specialised kernel; anything else returns cudaErrorNotSupported and the caller
 // uses the generic engine
 cudaError_t launch_nll_small(const NllArgs& a, int mode, cudaStream_t st) {
     const int NT = a.npad / 8;
-    if (a.k > 8 || NT > 16 || a.C <= 0) return cudaErrorNotSupported;
+    if (a.k > 8 || NT > 18 || a.C <= 0) return cudaErrorNotSupported;
     if (a.k > 4) return launch_nll_small_k8(a, mode, st);
     if (NT <= 2) return launch_small_k<2>(a, mode, st);
     if (NT <= 4) return launch_small_k<4>(a, mode, st);
     if (NT <= 6) return launch_small_k<6>(a, mode, st);
     if (NT <= 8) return launch_small_k<8>(a, mode, st);
     if (NT <= 12) return launch_small_k<12>(a, mode, st);  // 64 < n <= 96: 9 warps per SM
-    return launch_small_k<16>(a, mode, st);                 // 96 < n <= 128: 5 warps per SM
+    if (NT <= 16) return launch_small_k<16>(a, mode, st);  // 96 < n <= 128: 5 warps per SM
+    return launch_small_k<18>(a, mode, st);                 // 128 < n <= 144: 4 warps per SM
 }
 #endif
 

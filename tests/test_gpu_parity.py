@@ -217,7 +217,7 @@ def test_c3_n1024_k8(gold, K):
 @pytest.mark.parametrize('n,k_', [(1, 1), (2, 1), (7, 2), (13, 3), (30, 6), (64, 8), (65, 2), (73, 2), (80, 5), (100, 7), (90, 4), (96, 3), (97, 2), (104, 2), (128, 4), (129, 4), (144, 2),
                                   (225, 3), (230, 16)])
 def test_ragged_sizes_against_oracle(K, n, k_):
-    """sizes straddling every kernel variant / padding boundary (8-tiles; n <= 128 and k <= 8 warp-per-candidate,
+    """sizes straddling every kernel variant / padding boundary (8-tiles; n <= 144 and k <= 8 warp-per-candidate,
     n <= 128 with k > 8: CTA in shared memory, <= 144 macro-panel kernel, beyond: dataflow kernel)"""
     rng = np.random.default_rng(n * 100 + k_)
     X = rng.uniform(0, 10, (n, k_))

@@ -12,7 +12,7 @@ from mylibs.kriging import Kriging  # noqa: E402
 from sm_b200 import _cabi, device, workloads  # noqa: E402
 
 L = _cabi.lib()
-for n, k, C in [(64, 2, 100000), (64, 8, 50000), (36, 6, 100000), (96, 8, 20000), (128, 8, 20000), (96, 2, 50000), (128, 2, 20000)]:
+for n, k, C in [(128, 2, 20000), (136, 2, 20000), (144, 2, 20000), (144, 8, 20000), (152, 2, 20000)]:
     X, y = workloads.c3_lhs1024(n=n, k=k)
     e, p = workloads.c3_candidates(C, k)
     kr = Kriging(X * 10, y)
