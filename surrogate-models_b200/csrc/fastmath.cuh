@@ -188,8 +188,16 @@ __device__ __forceinline__ double pow_pos(double x, double p, const PowTables& T
 // + ONE third-order (Halley) step  y <- y (1 + e/2 + 3 e^2 / 8),  e = 1 - d y^2  -> rel. error ~3e-22 before
 // the final rounding.  8 instructions against 14 (with branches) for CUDA's rsqrt(double); it sits on the
 // critical path of every 8x8 diagonal-tile step.  d <= 0 / NaN give NaN (callers flag those pivots anyway).
+// seed of 1/sqrt(d): MUFU.RSQ64H on the double itself (rel. error ~1e-6) -- one instruction instead of
+// cvt.f32 + MUFU.RSQ + cvt.f64 on the critical chain of every pivot
+__device__ __forceinline__ double rsqrt_seed(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;\n" : "=d"(y) : "d"(d));
+    return y;
+}
+
 __device__ __forceinline__ double rsqrt_pivot(double d) {
-    double y = (double)rsqrtf((float)d);
+    double y = rsqrt_seed(d);
     const double e = fma(-(d * y), y, 1.0);
     const double p = fma(0.375, e, 0.5);
     return fma(y * e, p, y);

@@ -148,7 +148,7 @@ __device__ __forceinline__ bool diag_factor(double c0, double c1, double* __rest
         //   1/d = y^2 (1 + e + e^2) + O(e^3),   1/sqrt(d) = y (1 + e/2 + 3 e^2 / 8) + O(e^3)
         ok = ok && (d > 1e-36);  // below that R is numerically singular (and the fp32 seed would underflow)
         tp *= d;
-        const double y = (double)rsqrtf((float)d);
+        const double y = rsqrt_seed(d);
         const double y2 = y * y;
         const double e = fma(-d, y2, 1.0);
         const double inv2 = fma(y2, fma(e, e, e), y2);
