@@ -76,7 +76,9 @@ int sm_krig_nll_batch_host(const double* X, const double* y, int n, int k, const
  * Replaces Kriging.update_param (mylibs/kriging.py:53-63 = _calc_cormat :66-84 + _calc_mu :86-93) and
  * calc_likelihood (:95-116).  scalars[4] = {nll, mu, sigma2, info}; info 1 = not numerically SPD.
  * w[n] = R^-1 (y - 1 mu); b[npad] = L^-1 1; rres[npad] = L^-1 (y - 1 mu); Mop[sm_krig_mop_doubles(n)] =
- * L^-1 as packed 8x8 operand tiles (consumed by sm_krig_predict for the MSE); R[n*n] optional (NULL). */
+ * L^-1 as packed 8x8 operand tiles (consumed by sm_krig_predict for the MSE); R[n*n] optional (NULL).
+ * Mop may be NULL (weights only: no MSE afterwards); for n > 144 the fit then runs on the batched likelihood
+ * kernel plus a back-substitution instead of the single-CTA factorisation with identity right-hand sides. */
 int sm_krig_fit(const double* X, const double* y, int n, int k, const double* theta, const double* p,
                 double* scalars, double* w, double* b, double* rres, double* Mop, double* R, void* stream);
 

@@ -172,11 +172,22 @@ int sm_krig_nll_batch(const double* X, const double* y, int n, int k, const doub
 
 int sm_krig_fit(const double* X, const double* y, int n, int k, const double* theta, const double* p,
                 double* scalars, double* w, double* b, double* rres, double* Mop, double* R, void* stream) {
-    if (!X || !y || !theta || !p || !scalars || !w || !b || !rres || !Mop || bad_nk(n, k)) return SM_E_BADARG;
+    if (!X || !y || !theta || !p || !scalars || !w || !b || !rres || bad_nk(n, k)) return SM_E_BADARG;
     keep_pool_cached();
     Launches L;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!Mop && nll_uses_flow(n)) {  // weights only, n > 144: dataflow kernel + back-substitution
+        FitOut out{scalars, w, b, rres, nullptr, R};
+        SM_TRY(launch_krig_fit_weights(X, y, n, k, theta, p, out, st, &L.n));
+        return 0;
+    }
+    DevBuf mtmp(st);
+    if (!Mop) {  // weights only at small n: the full fit is cheap, its L^-1 goes to a scratch buffer
+        SM_TRY(mtmp.alloc(sm_krig_mop_doubles(n) * 8));
+        Mop = mtmp.as<double>();
+    }
     FitOut out{scalars, w, b, rres, Mop, R};
-    SM_TRY(launch_krig_fit(X, y, n, k, theta, p, out, (cudaStream_t)stream, &L.n));
+    SM_TRY(launch_krig_fit(X, y, n, k, theta, p, out, st, &L.n));
     return 0;
 }
 

@@ -27,6 +27,7 @@ struct NllArgs {
     // output / scratch
     double* nll_out;    // [C]
     double* workspace;  // tile storage for the global-memory variant
+    int keep_factor;    // krig_nll_flow.cu: also store the factor of the diagonal blocks (single-model fit)
     int l2mode;         // krig_nll_flow.cu: L2 eviction policies, 2 bits each: A strips | B strips << 2 | tables << 4
 };
 
@@ -48,6 +49,7 @@ bool nll_uses_flow(int n);
 cudaError_t launch_log2tab(const double* X, int n, int k, int npad, double* LG, cudaStream_t st);  // tile-packed, [flow_table_doubles(n)][k]
 cudaError_t launch_dtab_packed(const double* X, int n, int k, int npad, const double* p_axis, int P, double* D, cudaStream_t st);
 size_t flow_table_doubles(int n);  // doubles of ONE tile-packed lower-triangle table
+size_t flow_workspace_doubles(int n);  // doubles of one candidate's workspace: (4 NB + 1) tile rows of NT tiles
 cudaError_t launch_dtab(const double* X, int n, int k, int npad, const double* p_axis, int P, double* D, cudaStream_t st);
 cudaError_t launch_egrid(const double* dtab, const double* theta_axis, int k, int P, int T, int npad, double* E, cudaStream_t st);
 cudaError_t launch_logtab(const double* X, int n, int k, int npad, double* LG, cudaStream_t st);
@@ -64,6 +66,9 @@ struct FitOut {
     double* R;        // optional [n][n] correlation matrix (may be null)
 };
 size_t fit_tile_doubles(int n);
+// weights-only fit for n > 144 (no Mop): dataflow kernel on one candidate + back-substitution on the kept factor
+cudaError_t launch_krig_fit_weights(const double* X, const double* y, int n, int k, const double* theta, const double* p,
+                                    FitOut out, cudaStream_t st, long long* launches);
 cudaError_t launch_krig_fit(const double* X, const double* y, int n, int k, const double* theta, const double* p,
                             FitOut out, cudaStream_t st, long long* launches);
 

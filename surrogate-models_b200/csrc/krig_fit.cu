@@ -143,6 +143,139 @@ __global__ void corr_matrix_kernel(const double* __restrict__ X, int n, int k, c
     }
 }
 
+// ------------------------------------------------------------------------------------ weights-only fit, n > 144
+// The dataflow likelihood kernel (krig_nll_flow.cu) runs on ONE candidate with keep_factor set and leaves in the
+// workspace: L (tile (I, K) at (I NT + K) * 64 doubles, operand order, diagonal blocks included) and, in tile row 4 NB,
+// a = L^-1 y (row 0) and b = L^-1 1 (row 1).  This kernel (one CTA) derives mu, sigma^2, rres = a - mu b and
+// back-substitutes L^T w = rres.  nll comes from the likelihood kernel itself (scalars[0]).
+__global__ void __launch_bounds__(256) krig_backsolve_kernel(const double* __restrict__ ws, int n, FitOut out) {
+    extern __shared__ double x_s[];  // [npad]
+    __shared__ double red[3][8];
+    __shared__ double xj[8];
+    const int NT = (n + 7) / 8, npad = NT * 8, NB = (NT + 3) / 4;
+    const size_t rowstride = (size_t)NT * 64;
+    const double* rhs = ws + (size_t)(4 * NB) * rowstride;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (!(out.scalars[0] < INFINITY)) {  // not numerically SPD (or NaN): in-band, like the full fit
+        if (threadIdx.x == 0) {
+            out.scalars[0] = INFINITY;
+            out.scalars[1] = NAN;
+            out.scalars[2] = NAN;
+            out.scalars[3] = 1.0;
+        }
+        return;
+    }
+    double sab = 0.0, sbb = 0.0;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const double* t = rhs + (size_t)(j >> 3) * 64;
+        const double av = t[tile_pos(0, j & 7)], bv = t[tile_pos(1, j & 7)];
+        sab = fma(av, bv, sab);
+        sbb = fma(bv, bv, sbb);
+    }
+    sab = warp_sum(sab);
+    sbb = warp_sum(sbb);
+    if (lane == 0) {
+        red[0][wid] = sab;
+        red[1][wid] = sbb;
+    }
+    __syncthreads();
+    double tab_ = 0.0, tbb = 0.0;
+    for (int i = 0; i < 8; ++i) {
+        tab_ += red[0][i];
+        tbb += red[1][i];
+    }
+    const double mu = tab_ / tbb;
+    double srr = 0.0;
+    for (int j = threadIdx.x; j < npad; j += blockDim.x) {
+        const double* t = rhs + (size_t)(j >> 3) * 64;
+        const double av = (j < n) ? t[tile_pos(0, j & 7)] : 0.0, bv = (j < n) ? t[tile_pos(1, j & 7)] : 0.0;
+        const double rj = fma(-mu, bv, av);
+        out.b[j] = bv;
+        out.rres[j] = rj;
+        x_s[j] = rj;
+        srr = fma(rj, rj, srr);
+    }
+    srr = warp_sum(srr);
+    if (lane == 0) red[2][wid] = srr;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; ++i) t += red[2][i];
+        out.scalars[1] = mu;
+        out.scalars[2] = t / n;
+        out.scalars[3] = 0.0;
+    }
+    // back-substitution, block row by block row from the bottom
+    for (int J = NT - 1; J >= 0; --J) {
+        const double* rowJ = ws + (size_t)J * rowstride;
+        if (threadIdx.x == 0) {  // 8 x 8 upper-triangular solve with L_JJ^T
+            const double* D = rowJ + (size_t)J * 64;
+            double v[8];
+            for (int c = 0; c < 8; ++c) v[c] = x_s[8 * J + c];
+            for (int c = 7; c >= 0; --c) {
+                double s = v[c];
+                for (int rr = c + 1; rr < 8; ++rr) s = fma(-D[tile_pos(rr, c)], v[rr], s);
+                const double dcc = D[tile_pos(c, c)];
+                v[c] = (8 * J + c < n) ? s / dcc : 0.0;
+            }
+            for (int c = 0; c < 8; ++c) {
+                xj[c] = v[c];
+                x_s[8 * J + c] = v[c];
+            }
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < 8 * J; t += blockDim.x) {  // x_K -= L_JK^T x_J for K < J
+            const double* T = rowJ + (size_t)(t >> 3) * 64;
+            const int c = t & 7;
+            double s = x_s[t];
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr) s = fma(-T[tile_pos(rr, c)], xj[rr], s);
+            x_s[t] = s;
+        }
+        __syncthreads();
+    }
+    for (int j = threadIdx.x; j < n; j += blockDim.x) out.w[j] = x_s[j];
+}
+
+cudaError_t launch_krig_fit_weights(const double* X, const double* y, int n, int k, const double* theta, const double* p,
+                                    FitOut out, cudaStream_t st, long long* launches) {
+    const int npad = (n + 7) / 8 * 8;
+    double *ws = nullptr, *tab = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&ws, flow_workspace_doubles(n) * 8, st);
+    if (e != cudaSuccess) return e;
+    e = cudaMallocAsync((void**)&tab, flow_table_doubles(n) * k * 8, st);
+    if (e == cudaSuccess) e = launch_log2tab(X, n, k, npad, tab, st);
+    if (e == cudaSuccess) {
+        NllArgs a{};
+        a.X = X; a.y = y; a.n = n; a.k = k; a.npad = npad;
+        a.C = 1; a.c_begin = 0;
+        a.theta = theta; a.p = p; a.log2tab = tab;
+        a.nll_out = out.scalars;  // scalars[0] = nll
+        a.workspace = ws;
+        a.keep_factor = 1;
+        e = launch_nll_flow(a, 1, st);
+    }
+    if (e == cudaSuccess) {
+        const size_t smem = (size_t)npad * 8;
+        e = cudaFuncSetAttribute(krig_backsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) {
+            krig_backsolve_kernel<<<1, 256, smem, st>>>(ws, n, out);
+            e = cudaGetLastError();
+        }
+    }
+    if (launches) *launches += 3;
+    if (e == cudaSuccess && out.R) {
+        int grid = (int)(((size_t)n * n + 255) / 256);
+        if (grid > 148 * 8) grid = 148 * 8;
+        corr_matrix_kernel<<<grid, 256, 0, st>>>(X, n, k, theta, p, out.R);
+        e = cudaGetLastError();
+        if (launches) *launches += 1;
+    }
+    if (tab) cudaFreeAsync(tab, st);
+    cudaError_t e2 = cudaFreeAsync(ws, st);
+    return e != cudaSuccess ? e : e2;
+}
+
 cudaError_t launch_krig_fit(const double* X, const double* y, int n, int k, const double* theta, const double* p,
                             FitOut out, cudaStream_t st, long long* launches) {
     double* tiles = nullptr;

@@ -489,6 +489,18 @@ __device__ __forceinline__ bool flow_task_p(FlowCtl& S, const NllArgs& a, double
     FPH_MARK(4);
     if (!ok) return false;
 
+    if (a.keep_factor) {  // single-model fit: the factor of the diagonal block goes into its (otherwise unused) tile slots
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+            for (int jj = 0; jj <= ii; ++jj)
+                if (ii < nrow) {
+                    double2 v;
+                    v.x = (ii > jj || r >= q) ? Sm[(8 * jj + q) * 32 + 8 * ii + r] : 0.0;
+                    v.y = (ii > jj || r >= q + 4) ? Sm[(8 * jj + q + 4) * 32 + 8 * ii + r] : 0.0;
+                    *reinterpret_cast<double2*>(tiles + G.tile_off(4 * b + ii, 4 * b + jj) + 2 * lane) = v;
+                }
+    }
     if (b >= 2) wait_ge(&S.coldone[b - 2], G.NB - (b - 2));  // the slot's previous users are done
     FPH_MARK(5);
     double* const Wb = S.W[b & 1];
@@ -715,6 +727,7 @@ __global__ void dtab_packed_kernel(const double* __restrict__ X, int n, int k, s
         D[t] = v;
     }
 }
+size_t flow_workspace_doubles(int n) { return flow_ws_doubles((n + 7) / 8); }
 size_t flow_table_doubles(int n) {
     const size_t NT = (size_t)(n + 7) / 8;
     return NT * (NT + 1) / 2 * 64;
@@ -762,6 +775,11 @@ static cudaError_t launch_flow_t(NllArgs a, int mode, cudaStream_t st) {
     if (grid > a.C) grid = a.C;
     const long long ws_cap = (long long)(((size_t)24 << 30) / tile_bytes);
     if (grid > ws_cap) grid = ws_cap > 0 ? ws_cap : 1;
+    if (a.workspace) {  // caller-owned workspace of ONE candidate (single-model fit keeps the factor)
+        if (a.C != 1) return cudaErrorInvalidValue;
+        kern<<<1, LW * 32, smem, st>>>(a);
+        return cudaGetLastError();
+    }
     double* ws = nullptr;
     e = cudaMallocAsync((void**)&ws, (size_t)grid * tile_bytes, st);
     if (e != cudaSuccess) return e;

@@ -699,6 +699,38 @@ def test_randomised_parity_sweep():
     assert 'NONFINITE-MISMATCH' not in r.stdout
 
 
+@pytest.mark.parametrize('n,k_', [(150, 2), (361, 5), (1024, 8)])
+def test_weights_only_fit_large_n(K, n, k_):
+    """n >= 145: update_param runs the weights-only fit (dataflow kernel on one candidate + back-substitution on the
+    kept factor); it must leave the same state as the full single-CTA fit, and the MSE operand appears on demand"""
+    rng = np.random.default_rng(n + k_)
+    X = rng.uniform(0, 10, (n, k_))
+    y = np.sin(X.sum(axis=1)) + 0.1 * X[:, 0] ** 2
+    th, p = 10. ** rng.uniform(-1.5, 0.0, k_), rng.uniform(1.2, 1.9, k_)
+    a = K(X, y)
+    a.update_param(th, p)
+    assert a._fit['Mop'] is None                                  # weights only
+    full = a._run_fit(want_mse=True)
+    cond = orc.cond2(orc.corr_matrix(X, th, p))
+    t = float(tol(cond)) * 10
+    assert rel(a._fit['nll'], full['nll']) < t and rel(a._fit['mu'], full['mu']) < t
+    assert rel(a._fit['sigma2'], full['sigma2']) < t
+    wa, wf = a._fit['w'].cpu().numpy(), full['w'].cpu().numpy()
+    assert np.max(np.abs(wa - wf)) <= t * np.max(np.abs(wf))
+    assert rel(a.calc_likelihood(), orc.nll_chol(X, y, th, p)) < t
+    xq = rng.uniform(0, 10, (20, k_))
+    xq[0] = X[3]
+    yr, mr = orc.predict_chol(X, y, th, p, xq, True)
+    assert np.max(rel(a.predict_batch(xq), yr)) < t * 10
+    assert rel(a.predict_batch(xq)[0], y[3]) < 1e-6             # interpolation
+    yy, mse = a.predict_batch(xq[:6], return_mse=True)            # triggers the L^-1 computation
+    assert a._fit['Mop'] is not None
+    assert np.max(rel(yy, yr[:6])) < t * 10 and np.max(np.abs(mse - mr[:6])) < t * 10 * max(a._fit['sigma2'], 1e-300)
+    # not numerically SPD -> in band
+    a.update_param(np.full(k_, 1e-9), np.full(k_, 2.0))
+    assert a.calc_likelihood() == np.inf and not a._fit['ok']
+
+
 def test_optimize_grid_end_to_end_r3(gold, K, capsys):
     """Kriging.optimize('grid') end to end on kriging_r3 (n = 36, k = 2): batched grid, then SciPy SLSQP on
     single evaluations exactly like the reference (likeli_optimizer.py:37-48).  The optimum sits at
