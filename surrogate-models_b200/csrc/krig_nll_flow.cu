@@ -817,11 +817,13 @@ cudaError_t launch_nll_flow(NllArgs a, int mode, cudaStream_t st) {
     a.l2mode = l2;
     const int NT = a.npad / 8;
     int sel = cfg ? cfg : (NT < 192 ? 42 : 63);  // 4 warps x 4 CTAs below n = 1536, 6 warps x 2 CTAs (168 registers) above
-    if (!cfg && a.C <= sm_count()) sel = 73;  // fewer candidates than SMs (optimiser objective: C = 1): latency -- most warps per candidate
+    if (!cfg && a.C <= sm_count()) sel = (NT >= 64) ? 162 : 73;  // fewer candidates than SMs (optimiser objective, fit: C = 1):
+                                                                  // latency -- most warps per candidate
     switch (sel) {  // (2 .. 7 warps per CTA at 12 - 16 warps per SM all measured within 5 % of each other)
         case 42: return launch_flow_t<4, 2, 4>(a, mode, st);
         case 43: return launch_flow_t<4, 3, 3>(a, mode, st);   // 12 warps / SM, 168 registers
         case 73: return launch_flow_t<7, 3, 2>(a, mode, st);   // 14 warps / SM, 144 registers
+        case 162: return launch_flow_t<16, 2, 1>(a, mode, st); // one 16-warp CTA per SM: single-candidate latency
         default: return launch_flow_t<6, 3, 2>(a, mode, st);   // 63: 12 warps / SM, 168 registers
     }
 }
