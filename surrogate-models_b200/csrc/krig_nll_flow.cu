@@ -412,7 +412,72 @@ __device__ __forceinline__ void flow_task_u(FlowCtl& S, const NllArgs& a, double
 }
 
 // ---------------------------------------------------------------------------------------------- task P(b)
-// returns false when a pivot is not positive
+// 8 x 8 Cholesky + inverse of one diagonal tile.  In: the tile in accumulator layout (c0, c1).  Out: W = L^-1 in
+// operand order in `wt` (the B operand of the panel products and of the U solves), the product of the 8 pivots in
+// `tp`, optionally L itself in `lt` (operand order, single-model fit); false on a pivot <= 1e-30 / NaN.
+// Same scheme as the warp-per-candidate kernel (krig_nll_small.cu, diag_factor): the pivot travels by ONE shuffle from
+// the register that holds the updated diagonal element, everything else of a step is broadcast through the
+// column-major scratch `ts` and is off the serial chain; the rank-1 update of W runs one step late so that one
+// __syncwarp per step suffices.  14 fp64-pipe instructions per pivot -- the lane-per-row 32 x 32 factorisation this
+// replaces issued ~35 per pivot, and on a scheduler shared with DMMA-issuing warps every one of them queues behind
+// 16-cycle tensor instructions (the block factorisation is the serial chain of the whole candidate).
+__device__ __forceinline__ bool flow_diag_factor(double c0, double c1, double* __restrict__ ts, double* __restrict__ wt,
+                                                 double* __restrict__ lt, double& tp, const int lane) {
+    const int r = lane >> 2, q = lane & 3;
+    const int p0 = 2 * ((2 * q) & 3) + (q >> 1);  // tile_pos(i, 2q) - 8 i; column 2q + 1 sits 2 doubles later
+    bool ok = true;
+    double w0 = (r == 2 * q) ? 1.0 : 0.0, w1 = (r == 2 * q + 1) ? 1.0 : 0.0;
+    ts[(2 * q) * 8 + r] = c0;
+    ts[(2 * q + 1) * 8 + r] = c1;
+    tp = 1.0;
+    double lrw_prev = 0.0;
+    double d = __shfl_sync(0xffffffffu, c0, 0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        __syncwarp();  // column j of ts and row j-1 of wt are visible
+        double wj0 = 0.0, wj1 = 0.0;
+        if (j > 0) {
+            wj0 = wt[8 * (j - 1) + p0];
+            wj1 = wt[8 * (j - 1) + p0 + 2];
+        }
+        const double vr = ts[j * 8 + r];
+        const double2 vc = *reinterpret_cast<const double2*>(ts + j * 8 + 2 * q);
+        ok = ok && (d > 1e-30);  // also false for NaN
+        tp *= d;
+        // 1/d and 1/sqrt(d) from one seed y ~ d^-1/2, e = 1 - d y^2:  1/d = y^2 (1 + e + e^2),  d^-1/2 = y (1 + e/2 + 3 e^2/8)
+        const double y = rsqrt_seed(d);
+        const double y2 = y * y;
+        const double e = fma(-d, y2, 1.0);
+        const double inv2 = fma(y2, fma(e, e, e), y2);
+        const double t = vr * inv2;
+        c0 = fma(-t, vc.x, c0);
+        c1 = fma(-t, vc.y, c1);
+        if (j < 7) d = __shfl_sync(0xffffffffu, ((j + 1) & 1) ? c1 : c0, 4 * (j + 1) + ((j + 1) >> 1));
+        // off the critical chain from here
+        const double inv = fma(y, e * fma(0.375, e, 0.5), y);
+        if (j > 0 && r > j - 1) {  // delayed rank-1 update of W with row j-1 (final since the previous step)
+            w0 = fma(-lrw_prev, wj0, w0);
+            w1 = fma(-lrw_prev, wj1, w1);
+        }
+        lrw_prev = vr * inv;  // L[r][j]
+        if (lt != nullptr && q == 0 && r >= j) lt[tile_pos(r, j)] = lrw_prev;
+        if (r == j) {  // row j of W is final
+            wt[8 * r + p0] = w0 * inv;
+            wt[8 * r + p0 + 2] = w1 * inv;
+        }
+        if (j < 7 && q == ((j + 1) >> 1)) ts[(j + 1) * 8 + r] = ((j + 1) & 1) ? c1 : c0;
+    }
+    __syncwarp();
+    return ok;
+}
+
+__device__ __forceinline__ double flip_sign(double x) {  // integer pipe, not an fp64 instruction
+    return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));
+}
+
+// Diagonal block b: D = R_bb - sum_k L_bk L_bk^T, then a right-looking tile Cholesky of the 32 x 32 block (4 x 4 tiles)
+// that leaves exactly what the U solves of this macro column read in the W slot: W_tt = L_tt^-1 on the diagonal and
+// -L_it below it.  Returns false when a pivot is not positive.
 template <int ST>
 __device__ __forceinline__ bool flow_task_p(FlowCtl& S, const NllArgs& a, double* __restrict__ tiles,
                                             double* __restrict__ wring, const int b, const int lane, double& logsum,
@@ -430,9 +495,10 @@ __device__ __forceinline__ bool flow_task_p(FlowCtl& S, const NllArgs& a, double
     FPH_MARK(2);
     wait_ge(&S.erow[b], b + 1);  // E(b, b) has parked the diagonal block's entries
     FPH_MARK(3);
-    // D = R - sum as a plain 32 x 32 block, column-major: Sm[c * 32 + i]
-    double* const Sm = wring;
-    double* const INV = S.inv;
+    // scratch (this warp's ring, idle now): the 10 lower tiles in operand order, tile (ii, jj) at slot ii (ii+1)/2 + jj
+    double* const scr = wring;
+    double* const ts = wring + 640;
+    double* const lt = a.keep_factor ? wring + 704 : nullptr;
     const double* const slots = tiles + 2 * lane;
 #pragma unroll
     for (int ii = 0; ii < 4; ++ii)
@@ -447,86 +513,50 @@ __device__ __forceinline__ bool flow_task_p(FlowCtl& S, const NllArgs& a, double
                 v0 = (ii == jj && r == 2 * q) ? 1.0 : 0.0;
                 v1 = (ii == jj && r == 2 * q + 1) ? 1.0 : 0.0;
             }
-            Sm[(8 * jj + 2 * q) * 32 + 8 * ii + r] = v0;
-            Sm[(8 * jj + 2 * q + 1) * 32 + 8 * ii + r] = v1;
+            st_acc(scr + (ii * (ii + 1) / 2 + jj) * 64, lane, v0, v1);
         }
-    __syncwarp();
-
-    // Cholesky, lane = row i: L_ij = (D_ij - sum_{c<j} L_ic L_jc) / L_jj.  The part of the sum that does not need
-    // column j-1 (c < j-1) is accumulated one step early, under the latency of the pivot's reciprocal square root.
-    bool ok = true;
-    double prod = 1.0, part = 0.0;
+    if (lt != nullptr) lt[2 * lane] = lt[2 * lane + 1] = 0.0;
+    if (b >= 2) wait_ge(&S.coldone[b - 2], G.NB - (b - 2));  // the W slot's previous users are done
+    FPH_MARK(5);
+    double* const Wb = S.W[b & 1];
     logsum = 0.0;
 #pragma unroll 1
-    for (int j = 0; j < 32; ++j) {
-        double aij = Sm[j * 32 + lane] - part;
-        if (j > 0) aij = fma(-Sm[(j - 1) * 32 + lane], Sm[(j - 1) * 32 + j], aij);
-        const double d = __shfl_sync(0xffffffffu, aij, j);
-        ok = ok && (d > 1e-30);  // also false for NaN
-        const double inv = rsqrt_pivot(d);
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        if (j < 31) {
-            const double* cj = Sm + j + 1;
-            int c = 0;
-            for (; c + 4 <= j; c += 4) {
-                s0 = fma(Sm[c * 32 + lane], cj[c * 32], s0);
-                s1 = fma(Sm[(c + 1) * 32 + lane], cj[(c + 1) * 32], s1);
-                s2 = fma(Sm[(c + 2) * 32 + lane], cj[(c + 2) * 32], s2);
-                s3 = fma(Sm[(c + 3) * 32 + lane], cj[(c + 3) * 32], s3);
+    for (int t = 0; t < 4; ++t) {
+        const int tt = t * (t + 1) / 2 + t;
+        double c0, c1, tp;
+        ld_acc(scr + tt * 64, lane, c0, c1);  // own positions: no hazard with the updates of the previous step
+        if (!flow_diag_factor(c0, c1, ts, Wb + tt * 64, lt, tp, lane)) return false;
+        logsum += log(tp);
+        if (lt != nullptr && t < nrow)  // single-model fit: the factor goes into the block's (otherwise unused) tile slots
+            *reinterpret_cast<double2*>(tiles + G.tile_off(4 * b + t, 4 * b + t) + 2 * lane) = ld_frag(lt, lane);
+        const double2 w = ld_frag(Wb + tt * 64, lane);
+#pragma unroll 1
+        for (int i = t + 1; i < 4; ++i) {  // L_it = D_it W_tt^T
+            const double2 af = ld_frag(scr + (i * (i + 1) / 2 + t) * 64, lane);
+            double x0 = 0.0, x1 = 0.0;
+            dmma(x0, x1, af.x, w.x);
+            dmma(x0, x1, af.y, w.y);
+            st_acc(Wb + (i * (i + 1) / 2 + t) * 64, lane, -x0, -x1);
+            if (lt != nullptr && i < nrow) st_acc(tiles + G.tile_off(4 * b + i, 4 * b + t), lane, x0, x1);
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int i = t + 1; i < 4; ++i) {  // D_ij -= L_it L_jt^T, t < j <= i
+            const double2 nli = ld_frag(Wb + (i * (i + 1) / 2 + t) * 64, lane);
+#pragma unroll 1
+            for (int j = t + 1; j <= i; ++j) {
+                const double2 nlj = ld_frag(Wb + (j * (j + 1) / 2 + t) * 64, lane);
+                double u0, u1;
+                double* const dst = scr + (i * (i + 1) / 2 + j) * 64;
+                ld_acc(dst, lane, u0, u1);
+                dmma(u0, u1, nli.x, flip_sign(nlj.x));
+                dmma(u0, u1, nli.y, flip_sign(nlj.y));
+                st_acc(dst, lane, u0, u1);
             }
-            for (; c < j; ++c) s0 = fma(Sm[c * 32 + lane], cj[c * 32], s0);
         }
-        part = (s0 + s1) + (s2 + s3);
-        prod *= d;
-        if ((j & 7) == 7) {  // fold before the product of pivots can underflow
-            logsum += log(prod);
-            prod = 1.0;
-        }
-        if (lane == j) INV[j] = inv;
-        if (lane >= j) Sm[j * 32 + lane] = aij * inv;  // own element of column j: no cross-lane hazard
         __syncwarp();
     }
     FPH_MARK(4);
-    if (!ok) return false;
-
-    if (a.keep_factor) {  // single-model fit: the factor of the diagonal block goes into its (otherwise unused) tile slots
-#pragma unroll
-        for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-            for (int jj = 0; jj <= ii; ++jj)
-                if (ii < nrow) {
-                    double2 v;
-                    v.x = (ii > jj || r >= q) ? Sm[(8 * jj + q) * 32 + 8 * ii + r] : 0.0;
-                    v.y = (ii > jj || r >= q + 4) ? Sm[(8 * jj + q + 4) * 32 + 8 * ii + r] : 0.0;
-                    *reinterpret_cast<double2*>(tiles + G.tile_off(4 * b + ii, 4 * b + jj) + 2 * lane) = v;
-                }
-    }
-    if (b >= 2) wait_ge(&S.coldone[b - 2], G.NB - (b - 2));  // the slot's previous users are done
-    FPH_MARK(5);
-    double* const Wb = S.W[b & 1];
-    {   // W_tt = L_tt^-1 of the four 8 x 8 diagonal tiles: lane = (tile t, column m), forward substitution
-        const int t = lane >> 3, m = lane & 7;
-        double x[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            double s = (i == m) ? 1.0 : 0.0;
-#pragma unroll
-            for (int c = 0; c < i; ++c) s = fma(-Sm[(8 * t + c) * 32 + 8 * t + i], x[c], s);
-            x[i] = s * INV[8 * t + i];
-            Wb[(t * (t + 1) / 2 + t) * 64 + tile_pos(i, m)] = x[i];
-        }
-        // -L of the six off-diagonal tiles, operand order
-#pragma unroll
-        for (int jj = 1; jj < 4; ++jj)
-#pragma unroll
-            for (int mt = 0; mt < jj; ++mt) {
-                double2 v;
-                v.x = -Sm[(8 * mt + q) * 32 + 8 * jj + r];
-                v.y = -Sm[(8 * mt + q + 4) * 32 + 8 * jj + r];
-                *reinterpret_cast<double2*>(Wb + (jj * (jj + 1) / 2 + mt) * 64 + 2 * lane) = v;
-            }
-    }
-    __syncwarp();
     FPH_MARK(6);
     return true;
 }

@@ -50,7 +50,8 @@ def worker(spec):
         fin = np.isfinite(ref) & np.isfinite(got)
         err = float(np.max(np.abs(got[fin] - ref[fin]) / np.maximum(1, np.abs(ref[fin])))) if fin.any() else -1.0
         out['parity'].append({'n': n, 'k': k, 'C': C, 'relerr': err, 'nonfinite_match': bool(np.array_equal(np.isfinite(ref), np.isfinite(got))),
-                              'nfinite': int(fin.sum()), 'got0': float(got[0]), 'ref0': float(ref[0])})
+                              'nfinite': int(fin.sum()), 'got0': float(got[0]), 'ref0': float(ref[0]),
+                              'each': [float(abs(g_ - r_) / max(1, abs(r_))) if np.isfinite(g_) and np.isfinite(r_) else float(np.isfinite(g_)) - float(np.isfinite(r_)) for g_, r_ in zip(got, ref)]})
     for (n, k, T, P) in spec.get('grid', []):
         X = rng.uniform(0, 10, (n, k))
         y = np.sin(X.sum(axis=1)) + 0.1 * X[:, 0] ** 2

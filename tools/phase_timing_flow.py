@@ -18,7 +18,16 @@ e, p = workloads.c3_candidates(C, k)
 L = _cabi.lib()
 dX, dy, th, pd = device.to_dev(X), device.to_dev(y), device.to_dev(10. ** e), device.to_dev(p)
 out = device.empty(C)
-f = lambda: _cabi.check(L.sm_krig_nll_batch(device.ptr(dX), device.ptr(dy), n, k, device.ptr(th), device.ptr(pd), C, 0, device.ptr(out), None, None, device.stream()))
+f_list = lambda: _cabi.check(L.sm_krig_nll_batch(device.ptr(dX), device.ptr(dy), n, k, device.ptr(th), device.ptr(pd), C, 0, device.ptr(out), None, None, device.stream()))
+if len(sys.argv) > 4 and sys.argv[4] == 'grid':  # C = T^k P^k candidates sharing the |dx|^p tables
+    T, P = int(sys.argv[5]), int(sys.argv[6])
+    C = (T * P) ** k
+    ta, pa = device.to_dev(10. ** np.linspace(-2, 0.5, T)), device.to_dev(np.linspace(1., 2., P))
+    out = device.empty(C)
+    f = lambda: _cabi.check(L.sm_krig_nll_grid(device.ptr(dX), device.ptr(dy), n, k, device.ptr(ta), T, device.ptr(pa), P, 0, C,
+                                               device.ptr(out), None, None, device.stream()))
+else:
+    f = f_list
 f(); torch.cuda.synchronize()
 buf = np.zeros(16, dtype=np.uint64)
 L.smb_flow_phase_read.argtypes = [ctypes.c_void_p, ctypes.c_int]
