@@ -66,9 +66,9 @@ struct FlowCtl {
     double W[2][10 * 64];  // factor of the diagonal block of macro column b in slot b & 1 (see P / U)
     double th2[KMAX];      // theta * log2(e); 0 beyond k
     double pw[KMAX];       // 1 beyond k
-    long long off[KMAX];   // table offset of dimension d; beyond k: that of k - 1
-    double inv[32];        // 1 / L_jj of the diagonal block being factored (one P task at a time)
-    double logacc;         // sum of ln(pivot) = ln det R
+    unsigned off[KMAX];    // table offset (doubles) of dimension d; beyond k: that of k - 1 (the host checks the range)
+    double pmant[FLOW_MAXG];  // product of the 32 pivots of diagonal block b = pmant[b] * 2^pexp[b]; the logarithms are
+    int pexp[FLOW_MAXG];      // taken once per candidate in the epilogue (log() on the P chain delayed every solve)
     int pdone, next_task, failed, safe_p;
     int rowdone[FLOW_MAXG];  // macro columns finished (X stored) for this row group
     int coldone[FLOW_MAXG];  // U tasks finished in this macro column
@@ -132,22 +132,28 @@ struct FlowGeom {
 // one dimension as ONE coalesced 512-byte request (the row-major table cost 8 separate 64-byte pieces per request).
 //   MODE 1 (list): tab[(tri * k + d) * 64 + 2l] = 512 log2|dx_d|          off[d] = 64 d,  tstride = 64 k
 //   MODE 0 (grid): tab[((d * P + q) * ntri + tri) * 64 + 2l] = |dx_d|^p_q  off[d] selects (d, q_d), tstride = 64
-// A chunk = 4 dimensions x 2 entries is evaluated as ONE straight-line block so the 8 independent powers interleave;
-// the table values of the next two chunks are in flight meanwhile (three register buffers).  Dimensions k .. 4 ceil(k/4)
-// - 1 run with weight 0 (the per-candidate parameter arrays are padded).
-template <int MODE>
-__device__ __forceinline__ void flow_task_e(const FlowCtl& S, const NllArgs& a, double* __restrict__ tiles, const int b,
-                                            const int g, const int lane) {
-    const FlowGeom G(a);
+// A chunk = 4 dimensions x 2 entries is evaluated as ONE straight-line block so the 8 independent powers interleave.
+// Dimensions k .. 4 ceil(k/4) - 1 run with weight 0 (the per-candidate parameter arrays are padded).
+// Register pipeline without copies: a chunk first reduces its 8 table values to what the rest of the evaluation needs
+// (list mode: the range-reduced pair (t, r) of each power; grid mode: the weighted sums themselves), which frees the
+// buffer, reloads THE SAME buffer for the chunk NBUF ahead and only then finishes the evaluation.  (The previous form --
+// two buffers rotated by register moves, the slow-path powers in a rolled loop that forced the operands through
+// local memory -- executed ~350 instructions per chunk for 90 fp64 ones: the entry tasks were issue-bound, not
+// fp64-bound.)  One buffer: the load latency hides behind the rest of the chunk and the other warps.  (Grid mode, where
+// a chunk is a handful of instructions, measured with a statically unrolled ring of 1 / 2 / 4 buffers: n = 256:
+// 12.6 / 10.9 / 9.3 TFLOP/s, n = 512: 19.5 / 19.3 / 17.7, n = 1024: 24.0 / 23.9 / 24.2 -- code size beats prefetch depth.)
+template <int MODE, bool SAFE>
+__device__ __forceinline__ void flow_e_loop(const FlowCtl& S, const FlowGeom& G, const double* __restrict__ tab,
+                                            const unsigned tstride, const int nch, double* __restrict__ slots, const int b,
+                                            const int g) {
     const bool diag = (g == b);
     const int ntile = diag ? 10 : 16;
     const int nrow = min(4, G.NT - 4 * g), ncol = min(4, G.NT - 4 * b);
-    const double* const tab = (MODE == 0 ? a.dtab : a.log2tab) + 2 * lane;
-    const unsigned tstride = (MODE == 0) ? 64u : 64u * (unsigned)a.k;
-    const int nch = (a.k + 3) >> 2;
-    const bool safe_p = S.safe_p != 0;
-    double* const slots = tiles + 2 * lane;
-
+#ifndef FLOW_E_NBUF_GRID
+#define FLOW_E_NBUF_GRID 1
+#endif
+    constexpr int NBUF = (MODE == 0) ? FLOW_E_NBUF_GRID : 1;
+    const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52, as in pow2_fast
     auto tile_ij = [&](int e, int& ii, int& jj) {
         if (diag) {
             ii = (e >= 6) ? 3 : (e >= 3) ? 2 : (e >= 1) ? 1 : 0;
@@ -158,55 +164,70 @@ __device__ __forceinline__ void flow_task_e(const FlowCtl& S, const NllArgs& a, 
         }
     };
     int le = 0, lch = 0, ce = 0, cch = 0;  // load / compute cursors (tile, chunk)
+    unsigned lbase = 0;                    // table offset (doubles) of the tile being loaded
     double s0 = 0.0, s1 = 0.0;
     auto issue = [&](double2 (&buf)[4]) {
         if (le < ntile) {
-            int ii, jj;
-            tile_ij(le, ii, jj);
-            const unsigned I = 4 * g + min(ii, nrow - 1), J = 4 * b + min(jj, ncol - 1);  // clamped: always a real tile
-            const double* src = tab + (size_t)(I * (I + 1) / 2 + J) * tstride;
+            if (lch == 0) {
+                int ii, jj;
+                tile_ij(le, ii, jj);
+                const unsigned I = 4 * g + min(ii, nrow - 1), J = 4 * b + min(jj, ncol - 1);  // clamped: always a real tile
+                lbase = (I * (I + 1) / 2 + J) * tstride;
+            }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) buf[u] = __ldg(reinterpret_cast<const double2*>(src + S.off[4 * lch + u]));
+            for (int u = 0; u < 4; ++u) buf[u] = __ldg(reinterpret_cast<const double2*>(tab + (size_t)(lbase + S.off[4 * lch + u])));
             if (++lch == nch) {
                 lch = 0;
                 ++le;
             }
         }
     };
-    auto consume = [&](const double2 (&buf)[4]) {
-        double e0[4], e1[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            e0[u] = buf[u].x;
-            e1[u] = buf[u].y;
-        }
+    auto chunk = [&](double2 (&buf)[4]) {
+        double t0[4], t1[4], r0[4], r1[4];
+        double a0 = 0.0, a1 = 0.0;  // second partial sum per entry: shorter dependent chains
         if (MODE == 1) {
-            if (safe_p) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const double pd = S.pw[4 * cch + u];
-                    e0[u] = pow2_fast(pd, e0[u], S.etab);
-                    e1[u] = pow2_fast(pd, e1[u], S.etab);
-                }
-            } else {
-#pragma unroll 1
-                for (int u = 0; u < 4; ++u) {
-                    const double pd = S.pw[4 * cch + u];
-                    e0[u] = pow2_slow(pd, e0[u]);
-                    e1[u] = pow2_slow(pd, e1[u]);
+            for (int u = 0; u < 4; ++u) {
+                const double pd = S.pw[4 * cch + u];
+                if (SAFE) {  // first half of pow2_fast
+                    t0[u] = fma(pd, buf[u].x, MAGIC);
+                    t1[u] = fma(pd, buf[u].y, MAGIC);
+                    const double n0 = t0[u] - MAGIC, n1 = t1[u] - MAGIC;
+                    r0[u] = fma(pd, buf[u].x, -n0);
+                    r1[u] = fma(pd, buf[u].y, -n1);
+                } else {
+                    t0[u] = pow2_slow(pd, buf[u].x);
+                    t1[u] = pow2_slow(pd, buf[u].y);
                 }
             }
-        }
-        double t0 = 0.0, t1 = 0.0;  // two partial sums per entry: shorter dependent chains
+        } else {
 #pragma unroll
-        for (int u = 0; u < 4; u += 2) {
-            s0 = fma(S.th2[4 * cch + u], e0[u], s0);
-            s1 = fma(S.th2[4 * cch + u], e1[u], s1);
-            t0 = fma(S.th2[4 * cch + u + 1], e0[u + 1], t0);
-            t1 = fma(S.th2[4 * cch + u + 1], e1[u + 1], t1);
+            for (int u = 0; u < 4; u += 2) {
+                s0 = fma(S.th2[4 * cch + u], buf[u].x, s0);
+                s1 = fma(S.th2[4 * cch + u], buf[u].y, s1);
+                a0 = fma(S.th2[4 * cch + u + 1], buf[u + 1].x, a0);
+                a1 = fma(S.th2[4 * cch + u + 1], buf[u + 1].y, a1);
+            }
         }
-        s0 += t0;
-        s1 += t1;
+        issue(buf);  // the buffer is dead: refill it for the chunk NBUF ahead
+        if (MODE == 1) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (SAFE) {
+                    t0[u] = exp2_core(t0[u], r0[u], S.etab);
+                    t1[u] = exp2_core(t1[u], r1[u], S.etab);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u += 2) {
+                s0 = fma(S.th2[4 * cch + u], t0[u], s0);
+                s1 = fma(S.th2[4 * cch + u], t1[u], s1);
+                a0 = fma(S.th2[4 * cch + u + 1], t0[u + 1], a0);
+                a1 = fma(S.th2[4 * cch + u + 1], t1[u + 1], a1);
+            }
+        }
+        s0 += a0;
+        s1 += a1;
         if (cch == nch - 1) {
             int ii, jj;
             tile_ij(ce, ii, jj);
@@ -220,19 +241,28 @@ __device__ __forceinline__ void flow_task_e(const FlowCtl& S, const NllArgs& a, 
             ++ce;
         }
     };
-    // ONE copy of the chunk evaluation in the loop body (three unrolled copies made it 18 KB: larger than the
-    // instruction cache of a scheduler, and `no_instruction` became the top stall reason at n = 512); the three
-    // buffers rotate through register moves instead (two buffers: one chunk of loads in flight is enough, measured).
-    const int total = ntile * nch;
-    double2 b0[4], b1[4];
-    issue(b0);
-#pragma unroll 1
-    for (int x = 0; x < total; ++x) {
-        issue(b1);
-        consume(b0);
+    double2 buf[NBUF][4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) b0[u] = b1[u];
+    for (int i = 0; i < NBUF; ++i) issue(buf[i]);
+    const int total = ntile * nch;
+#pragma unroll 1
+    for (int x = 0; x < total; x += NBUF) {
+#pragma unroll
+        for (int i = 0; i < NBUF; ++i)
+            if (x + i < total) chunk(buf[i]);
     }
+}
+
+template <int MODE>
+__device__ __forceinline__ void flow_task_e(const FlowCtl& S, const NllArgs& a, double* __restrict__ tiles, const int b,
+                                            const int g, const int lane) {
+    const FlowGeom G(a);
+    const double* const tab = (MODE == 0 ? a.dtab : a.log2tab) + 2 * lane;
+    const unsigned tstride = (MODE == 0) ? 64u : 64u * (unsigned)a.k;
+    const int nch = (a.k + 3) >> 2;
+    double* const slots = tiles + 2 * lane;
+    if (MODE == 0 || S.safe_p != 0) flow_e_loop<MODE, true>(S, G, tab, tstride, nch, slots, b, g);
+    else flow_e_loop<MODE, false>(S, G, tab, tstride, nch, slots, b, g);
 }
 
 // ---------------------------------------------------------------------------------------------- k-loop
@@ -480,7 +510,7 @@ __device__ __forceinline__ double flip_sign(double x) {  // integer pipe, not an
 // -L_it below it.  Returns false when a pivot is not positive.
 template <int ST>
 __device__ __forceinline__ bool flow_task_p(FlowCtl& S, const NllArgs& a, double* __restrict__ tiles,
-                                            double* __restrict__ wring, const int b, const int lane, double& logsum,
+                                            double* __restrict__ wring, const int b, const int lane, double& pm, int& pe,
                                             long long& fph_t) {
     const FlowGeom G(a);
     const int r = lane >> 2, q = lane & 3;
@@ -519,14 +549,19 @@ __device__ __forceinline__ bool flow_task_p(FlowCtl& S, const NllArgs& a, double
     if (b >= 2) wait_ge(&S.coldone[b - 2], G.NB - (b - 2));  // the W slot's previous users are done
     FPH_MARK(5);
     double* const Wb = S.W[b & 1];
-    logsum = 0.0;
+    pm = 1.0;
+    pe = 0;
 #pragma unroll 1
     for (int t = 0; t < 4; ++t) {
         const int tt = t * (t + 1) / 2 + t;
         double c0, c1, tp;
         ld_acc(scr + tt * 64, lane, c0, c1);  // own positions: no hazard with the updates of the previous step
         if (!flow_diag_factor(c0, c1, ts, Wb + tt * 64, lt, tp, lane)) return false;
-        logsum += log(tp);
+        {   // tp is a positive normal number (8 pivots in (1e-30, ~1]): split off its exponent
+            const int hi = __double2hiint(tp);
+            pe += (hi >> 20) - 1023;
+            pm *= __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(tp));
+        }
         if (lt != nullptr && t < nrow)  // single-model fit: the factor goes into the block's (otherwise unused) tile slots
             *reinterpret_cast<double2*>(tiles + G.tile_off(4 * b + t, 4 * b + t) + 2 * lane) = ld_frag(lt, lane);
         const double2 w = ld_frag(Wb + tt * 64, lane);
@@ -590,7 +625,6 @@ __global__ void __launch_bounds__(LW * 32, CPS) krig_nll_flow_kernel(const NllAr
             S.pdone = 0;
             S.next_task = 0;
             S.failed = 0;
-            S.logacc = 0.0;
         }
         if (threadIdx.x < KMAX) {
             const int d = min((int)threadIdx.x, a.k - 1);
@@ -607,11 +641,11 @@ __global__ void __launch_bounds__(LW * 32, CPS) krig_nll_flow_kernel(const NllAr
                 }
                 S.th2[threadIdx.x] = real ? a.theta_axis[it % a.T] * LOG2E : 0.0;
                 S.pw[threadIdx.x] = 1.0;
-                S.off[threadIdx.x] = ((long long)d * a.P + (ip % a.P)) * (long long)ntri * 64;
+                S.off[threadIdx.x] = (unsigned)(((long long)d * a.P + (ip % a.P)) * (long long)ntri * 64);
             } else {
                 S.th2[threadIdx.x] = real ? a.theta[c * a.k + d] * LOG2E : 0.0;
                 S.pw[threadIdx.x] = real ? a.p[c * a.k + d] : 1.0;
-                S.off[threadIdx.x] = 64ll * d;
+                S.off[threadIdx.x] = 64u * (unsigned)d;
             }
         }
         __syncthreads();
@@ -693,11 +727,15 @@ __global__ void __launch_bounds__(LW * 32, CPS) krig_nll_flow_kernel(const NllAr
             {
                 const bool failed = *(volatile int*)&S.failed != 0;
                 bool ok = true;
-                double logsum = 0.0;
-                if (!failed) ok = flow_task_p<ST>(S, a, tiles, wring, b, lane, logsum, fph_t);
+                double pm = 1.0;
+                int pe = 0;
+                if (!failed) ok = flow_task_p<ST>(S, a, tiles, wring, b, lane, pm, pe, fph_t);
                 __syncwarp();
                 if (lane == 0) {
-                    if (!failed && ok) S.logacc += logsum;
+                    if (!failed && ok) {
+                        S.pmant[b] = pm;
+                        S.pexp[b] = pe;
+                    }
                     if (!ok) *(volatile int*)&S.failed = 1;
                     __threadfence_block();
                     *(volatile int*)&S.pdone = b + 1;
@@ -708,8 +746,12 @@ __global__ void __launch_bounds__(LW * 32, CPS) krig_nll_flow_kernel(const NllAr
         FPH_MARK(11);
         if (wid == 0) {
             double nll = INFINITY;
-            if (S.failed == 0)
-                nll = nll_epilogue(tiles + G.tile_off(4 * NB, 0), a.n, lane, 0.5 * S.logacc, nullptr, nullptr);
+            if (S.failed == 0) {
+                double ls = 0.0;  // ln det R = sum over the elimination pivots d = L_jj^2 of ln d
+                for (int j = lane; j < NB; j += 32) ls += log(S.pmant[j]) + (double)S.pexp[j] * 0.6931471805599453;
+                ls = warp_sum(ls);  // butterfly: the same bits in every lane, independent of task timing
+                nll = nll_epilogue(tiles + G.tile_off(4 * NB, 0), a.n, lane, 0.5 * ls, nullptr, nullptr);
+            }
             if (lane == 0) a.nll_out[(long long)blockIdx.x + (long long)iter * gridDim.x] = nll;
         }
     }
@@ -839,6 +881,11 @@ cudaError_t launch_nll_flow(NllArgs a, int mode, cudaStream_t st) {
     if (!nll_uses_flow(a.n)) return cudaErrorNotSupported;
     if (a.C <= 0) return cudaSuccess;
     if (mode == 1 && !a.log2tab) return cudaErrorInvalidValue;
+    {   // the entry tasks index the tables with 32-bit offsets (doubles)
+        const size_t nt = (size_t)(a.npad / 8), ntri = nt * (nt + 1) / 2;
+        const size_t tab_doubles = ntri * 64 * (size_t)a.k * (size_t)(mode == 0 ? a.P : 1);
+        if (tab_doubles >= ((size_t)1 << 32)) return cudaErrorInvalidValue;
+    }
     cudaError_t e = upload_e2tab();
     if (e != cudaSuccess) return e;
     static const int cfg = [] { const char* v = getenv("SMB_FLOW_CFG"); return v ? atoi(v) : 0; }();
