@@ -28,7 +28,7 @@ struct NllArgs {
     double* nll_out;    // [C]
     double* workspace;  // tile storage for the global-memory variant
     int keep_factor;    // krig_nll_flow.cu: also store the factor of the diagonal blocks (single-model fit)
-    int l2mode;         // krig_nll_flow.cu: L2 eviction policies, 2 bits each: A strips | B strips << 2 | tables << 4
+    int l2mode;         // krig_nll_flow.cu: bit 0 = evict_first L2 policy on the A strips
 };
 
 struct NllPlan {

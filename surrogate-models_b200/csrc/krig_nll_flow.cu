@@ -28,7 +28,7 @@
 // Every task's prerequisites precede it in the queue, so a warp that waits is always waiting for a task another warp
 // is already running: no deadlock.
 // Tuning knobs (environment, read once): SMB_FLOW_CFG = 42 | 43 | 63 | 73 (warps per CTA, ring depth), SMB_FLOW_L2
-// (bit 0: evict_first on the A strips, bits 4..: L2 prefetch distance), SMB_FLOW_MIN_NT (smallest tile count routed here).
+// (bit 0: evict_first on the A strips), SMB_FLOW_MIN_NT (smallest tile count routed here).
 #include "fastmath.cuh"
 #include "fastmath2.cuh"
 #include "tile_chol.cuh"
@@ -273,41 +273,36 @@ __device__ __forceinline__ void flow_task_e(const FlowCtl& S, const NllArgs& a, 
 template <int HI, bool DIAG, int ST>
 __device__ __forceinline__ void strip_update(double (&acc)[HI][4][2], const double* __restrict__ abase,
                                              const double* __restrict__ bbase, const unsigned rowstride, const int nk,
-                                             double* __restrict__ ring /* + 2 * lane */, const bool stream_a,
-                                             const int pf_lane, const int pfd) {
-    auto issue = [&](int K, int stage) {
+                                             double* __restrict__ ring /* + 2 * lane */, const bool stream_a) {
+    // running source pointers of the next k-step to copy (bytes): one 64-bit add per strip and step, the rows of a
+    // strip are rowstride * 8 bytes apart (32-bit offsets)
+    const char* anext = reinterpret_cast<const char*>(abase);
+    const char* bnext = reinterpret_cast<const char*>(bbase);
+    const unsigned rs8 = rowstride * 8u;
+    auto issue = [&](int stage) {
         // A strips are read once per macro column: evict_first keeps them from flushing the B strips and the tables
         // out of L2 (the policy is re-created here instead of living in two registers across the loop)
         const unsigned long long pol_a = make_policy(stream_a ? 1 : 0);
         double* dst = ring + stage * (8 * 64);
 #pragma unroll
-        for (int ii = 0; ii < HI; ++ii) fcp_async16(dst + ii * 64, abase + (size_t)(ii * rowstride + K * 64), pol_a);
+        for (int ii = 0; ii < HI; ++ii) fcp_async16(dst + ii * 64, anext + (size_t)(ii * rs8), pol_a);
+        anext += 512;
         if (!DIAG) {
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) fcp_async16(dst + (4 + jj) * 64, bbase + (size_t)(jj * rowstride + K * 64));
+            for (int jj = 0; jj < 4; ++jj) fcp_async16(dst + (4 + jj) * 64, bnext + (size_t)(jj * rs8));
+            bnext += 512;
         }
     };
 #pragma unroll
     for (int s = 0; s < ST - 1; ++s) {
-        if (s < nk) issue(s, s);
+        if (s < nk) issue(s);
         fcp_commit();
-    }
-    // L2 prefetch PFD k-steps ahead of the ring: ONE instruction per k-step covers the 8 operand tiles of a step
-    // (lane l -> 128-byte line l % 4 of tile l / 4).  With only ST - 1 steps in flight per warp the k-loop ran at
-    // the L2-miss latency (a step of 32 DMMAs is 512 pipe cycles, a miss under load ~2000).
-    const int pl = pf_lane;  // lane index
-    const double* pf = ((pl < 16) ? abase - 2 * pl + (size_t)((pl >> 2) * rowstride)
-                                  : bbase - 2 * pl + (size_t)(((pl - 16) >> 2) * rowstride)) + (pl & 3) * 16;
-    const bool pf_on = pfd > 0 && ((pl < 16) ? (pl >> 2) < HI : !DIAG);
-    if (pf_on) {
-        for (int K = ST - 1; K < min(nk, pfd); ++K) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(pf + (size_t)K * 64));
     }
     int st_rd = 0;
 #pragma unroll 1
     for (int K = 0; K < nk; ++K) {
         const int st_wr = (st_rd == 0) ? ST - 1 : st_rd - 1;
-        if (pf_on && K + pfd < nk) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(pf + (size_t)(K + pfd) * 64));
-        if (K + ST - 1 < nk) issue(K + ST - 1, st_wr);
+        if (K + ST - 1 < nk) issue(st_wr);
         fcp_commit();
         fcp_wait<ST - 1>();  // the copies of step K have landed
         const double* src = ring + st_rd * (8 * 64);
@@ -361,7 +356,7 @@ __device__ __forceinline__ void flow_task_u(FlowCtl& S, const NllArgs& a, double
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) acc[ii][jj][0] = acc[ii][jj][1] = 0.0;
     strip_update<HI, false, ST>(acc, tiles + G.tile_off(I0, 0) + 2 * lane, tiles + G.tile_off(4 * b, 0) + 2 * lane, G.rowstride,
-                                4 * b, wring + 2 * lane, (a.l2mode & 1) != 0, lane, a.l2mode >> 4);
+                                4 * b, wring + 2 * lane, (a.l2mode & 1) != 0);
     FPH_MARK(8);
     if (!is_rhs) wait_ge(&S.erow[g], b + 1);  // the block's entries are parked in its tile slots (lane order)
     FPH_MARK(9);
@@ -520,8 +515,7 @@ __device__ __forceinline__ bool flow_task_p(FlowCtl& S, const NllArgs& a, double
     for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) acc[ii][jj][0] = acc[ii][jj][1] = 0.0;
-    strip_update<4, true, ST>(acc, tiles + G.tile_off(4 * b, 0) + 2 * lane, tiles, G.rowstride, 4 * b, wring + 2 * lane, false, lane,
-                              a.l2mode >> 4);
+    strip_update<4, true, ST>(acc, tiles + G.tile_off(4 * b, 0) + 2 * lane, tiles, G.rowstride, 4 * b, wring + 2 * lane, false);
     FPH_MARK(2);
     wait_ge(&S.erow[b], b + 1);  // E(b, b) has parked the diagonal block's entries
     FPH_MARK(3);
@@ -889,7 +883,7 @@ cudaError_t launch_nll_flow(NllArgs a, int mode, cudaStream_t st) {
     cudaError_t e = upload_e2tab();
     if (e != cudaSuccess) return e;
     static const int cfg = [] { const char* v = getenv("SMB_FLOW_CFG"); return v ? atoi(v) : 0; }();
-    // bit 0: evict_first on the A strips; bits 4..: L2 prefetch distance in k-steps (0 = off)
+    // bit 0: evict_first on the A strips (an L2 prefetch ahead of the ring was measured without gain and removed)
     static const int l2 = [] { const char* v = getenv("SMB_FLOW_L2"); return v ? atoi(v) : 1; }();
     a.l2mode = l2;
     const int NT = a.npad / 8;
