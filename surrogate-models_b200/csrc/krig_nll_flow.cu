@@ -142,6 +142,8 @@ struct FlowGeom {
 // fp64-bound.)  One buffer: the load latency hides behind the rest of the chunk and the other warps.  (Grid mode, where
 // a chunk is a handful of instructions, measured with a statically unrolled ring of 1 / 2 / 4 buffers: n = 256:
 // 12.6 / 10.9 / 9.3 TFLOP/s, n = 512: 19.5 / 19.3 / 17.7, n = 1024: 24.0 / 23.9 / 24.2 -- code size beats prefetch depth.)
+// (ptxas hoists the refill above the reduction and pays 16 register moves for it; a software-pipelined form that
+// needs none -- loads of chunk x + 1, finish chunk x, reduce chunk x + 1 -- measured 1 - 3 % slower.)
 template <int MODE, bool SAFE>
 __device__ __forceinline__ void flow_e_loop(const FlowCtl& S, const FlowGeom& G, const double* __restrict__ tab,
                                             const unsigned tstride, const int nch, double* __restrict__ slots, const int b,
@@ -657,7 +659,8 @@ __global__ void __launch_bounds__(LW * 32, CPS) krig_nll_flow_kernel(const NllAr
             if (lane == 0) t = atomicAdd(&S.next_task, 1);
             t = __shfl_sync(0xffffffffu, t, 0);
             if (t >= total_tasks) break;
-            // decode the queue position: kind 0 = E, 1 = P, 2 = U
+            // decode the queue position: kind 0 = E, 1 = P, 2 = U  (a per-launch lookup table instead of this closed form
+            // measured no gain: the cost of a grab is the shared-memory atomic and the shuffle, not the arithmetic)
             int kind, b, g;
             if (t <= NB) {  // prologue: E(0,0) P(0) E(0,1..NB-1)
                 kind = (t == 1) ? 1 : 0;
