@@ -146,8 +146,8 @@ struct FlowGeom {
 // needs none -- loads of chunk x + 1, finish chunk x, reduce chunk x + 1 -- measured 1 - 3 % slower.)
 template <int MODE, bool SAFE>
 __device__ __forceinline__ void flow_e_loop(const FlowCtl& S, const FlowGeom& G, const double* __restrict__ tab,
-                                            const unsigned tstride, const int nch, double* __restrict__ slots, const int b,
-                                            const int g) {
+                                            const unsigned tstride, const int nch, const bool dense,
+                                            double* __restrict__ slots, const int b, const int g) {
     const bool diag = (g == b);
     const int ntile = diag ? 10 : 16;
     const int nrow = min(4, G.NT - 4 * g), ncol = min(4, G.NT - 4 * b);
@@ -156,31 +156,33 @@ __device__ __forceinline__ void flow_e_loop(const FlowCtl& S, const FlowGeom& G,
 #endif
     constexpr int NBUF = (MODE == 0) ? FLOW_E_NBUF_GRID : 1;
     const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52, as in pow2_fast
-    auto tile_ij = [&](int e, int& ii, int& jj) {
-        if (diag) {
-            ii = (e >= 6) ? 3 : (e >= 3) ? 2 : (e >= 1) ? 1 : 0;
-            jj = e - ii * (ii + 1) / 2;
-        } else {
-            ii = e >> 2;
-            jj = e & 3;
+    // tile cursors (ii, jj) of the block -- diagonal block: the 10 lower tiles row by row; ii == 4: past the end
+    auto advance = [&](int& ii, int& jj) {
+        if (++jj > (diag ? ii : 3)) {
+            jj = 0;
+            ++ii;
         }
     };
-    int le = 0, lch = 0, ce = 0, cch = 0;  // load / compute cursors (tile, chunk)
-    unsigned lbase = 0;                    // table offset (doubles) of the tile being loaded
+    int lii = 0, ljj = 0, lch = 0, cii = 0, cjj = 0, cch = 0;  // load / compute cursors (tile, chunk)
+    unsigned lbase = 0;                                        // table offset (doubles) of the tile being loaded
     double s0 = 0.0, s1 = 0.0;
     auto issue = [&](double2 (&buf)[4]) {
-        if (le < ntile) {
+        if (lii < 4) {
             if (lch == 0) {
-                int ii, jj;
-                tile_ij(le, ii, jj);
-                const unsigned I = 4 * g + min(ii, nrow - 1), J = 4 * b + min(jj, ncol - 1);  // clamped: always a real tile
+                const unsigned I = 4 * g + min(lii, nrow - 1), J = 4 * b + min(ljj, ncol - 1);  // clamped: always a real tile
                 lbase = (I * (I + 1) / 2 + J) * tstride;
             }
+            if (MODE == 1 && dense) {  // k % 4 == 0: the four dimensions of a chunk are 64 doubles apart, one address
+                const double2* src = reinterpret_cast<const double2*>(tab + (size_t)(lbase + 256u * (unsigned)lch));
 #pragma unroll
-            for (int u = 0; u < 4; ++u) buf[u] = __ldg(reinterpret_cast<const double2*>(tab + (size_t)(lbase + S.off[4 * lch + u])));
+                for (int u = 0; u < 4; ++u) buf[u] = __ldg(src + 32 * u);
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) buf[u] = __ldg(reinterpret_cast<const double2*>(tab + (size_t)(lbase + S.off[4 * lch + u])));
+            }
             if (++lch == nch) {
                 lch = 0;
-                ++le;
+                advance(lii, ljj);
             }
         }
     };
@@ -230,17 +232,13 @@ __device__ __forceinline__ void flow_e_loop(const FlowCtl& S, const FlowGeom& G,
         }
         s0 += a0;
         s1 += a1;
-        if (cch == nch - 1) {
-            int ii, jj;
-            tile_ij(ce, ii, jj);
-            if (ii < nrow && jj < ncol)
-                *reinterpret_cast<double2*>(slots + G.tile_off(4 * g + ii, 4 * b + jj)) =
+        if (++cch == nch) {  // the tile is complete
+            cch = 0;
+            if (cii < nrow && cjj < ncol)
+                *reinterpret_cast<double2*>(slots + G.tile_off(4 * g + cii, 4 * b + cjj)) =
                     make_double2(exp2_neg(s0, S.etab), exp2_neg(s1, S.etab));
             s0 = s1 = 0.0;
-        }
-        if (++cch == nch) {
-            cch = 0;
-            ++ce;
+            advance(cii, cjj);
         }
     };
     double2 buf[NBUF][4];
@@ -263,8 +261,9 @@ __device__ __forceinline__ void flow_task_e(const FlowCtl& S, const NllArgs& a, 
     const unsigned tstride = (MODE == 0) ? 64u : 64u * (unsigned)a.k;
     const int nch = (a.k + 3) >> 2;
     double* const slots = tiles + 2 * lane;
-    if (MODE == 0 || S.safe_p != 0) flow_e_loop<MODE, true>(S, G, tab, tstride, nch, slots, b, g);
-    else flow_e_loop<MODE, false>(S, G, tab, tstride, nch, slots, b, g);
+    const bool dense = (a.k & 3) == 0;
+    if (MODE == 0 || S.safe_p != 0) flow_e_loop<MODE, true>(S, G, tab, tstride, nch, dense, slots, b, g);
+    else flow_e_loop<MODE, false>(S, G, tab, tstride, nch, dense, slots, b, g);
 }
 
 // ---------------------------------------------------------------------------------------------- k-loop
