@@ -372,7 +372,7 @@ def run_gpu(args):
                 'finite_fraction': float(np.isfinite(nllg.cpu().numpy()).mean())}
     c3pt = large_n_point(1024, 1184)
     secondary_c3 = dict(c3pt, metric='kriging likelihood evaluations/s (n=1024, k=8, list mode)',
-                        kernel='krig_nll_flow_kernel<4,2,1,4> (dataflow kernel, every n > 144; <6,3,1,2> from n = 1536)',
+                        kernel='krig_nll_flow_kernel<6,3,1,2> (dataflow kernel, every n > 144; <4,2,1,4> below n = 1024)',
                         other_sizes=[large_n_point(256, 9472), large_n_point(512, 2368), large_n_point(2048, 296)],
                         grid_mode=large_n_grid_point(1024, 3, 8, 3))
     # C4: gaussian RBF, n = 4096: weight solve + evaluation at 2e6 points per GPU

@@ -889,7 +889,9 @@ cudaError_t launch_nll_flow(NllArgs a, int mode, cudaStream_t st) {
     static const int l2 = [] { const char* v = getenv("SMB_FLOW_L2"); return v ? atoi(v) : 1; }();
     a.l2mode = l2;
     const int NT = a.npad / 8;
-    int sel = cfg ? cfg : (NT < 192 ? 42 : 63);  // 4 warps x 4 CTAs below n = 1536, 6 warps x 2 CTAs (168 registers) above
+    // 4 warps x 4 CTAs (128 registers) below n = 1024, 6 warps x 2 CTAs (168 registers) from there (measured, list mode k = 8:
+    // n = 768: 18.3 vs 18.1 TFLOP/s, 1024: 20.3 vs 20.6, 1536: 21.5 vs 23.5, 2048: 21.0 vs 24.2)
+    int sel = cfg ? cfg : (NT < 128 ? 42 : 63);
     if (!cfg && a.C <= sm_count()) sel = (NT >= 64) ? 162 : 73;  // fewer candidates than SMs (optimiser objective, fit: C = 1):
                                                                   // latency -- most warps per candidate
     switch (sel) {  // (2 .. 7 warps per CTA at 12 - 16 warps per SM all measured within 5 % of each other)
