@@ -30,6 +30,21 @@ __device__ __forceinline__ void exp_table_init(double* tab, int tid, int nthread
     for (int j = tid; j < EXP_TAB; j += nthreads) tab[j] = EXP_T32[j];
 }
 
+// Table lookup T = tab[N & 31] (the table is in SHARED memory at every call site) and the exponent insert
+// hi + ((N >> 5) << 20), two integer instructions each as explicit PTX (the C forms compile to three each; same change
+// as exp2_core of fastmath2.cuh, measured there).
+__device__ __forceinline__ double exp_tab32(int N, const double* __restrict__ tab) {
+    double T;
+    const unsigned tb = (unsigned)__cvta_generic_to_shared(tab);
+    asm("{ .reg .b32 j;\n and.b32 j, %1, 31;\n mad.lo.u32 j, j, 8, %2;\n ld.shared.f64 %0, [j];\n }" : "=d"(T) : "r"(N), "r"(tb));
+    return T;
+}
+__device__ __forceinline__ double exp_scale32(double v, int N) {  // v * 2^(N >> 5) by exponent arithmetic
+    int hi;
+    asm("{ .reg .b32 x;\n shr.s32 x, %1, 5;\n mad.lo.s32 %0, x, 1048576, %2;\n }" : "=r"(hi) : "r"(N), "r"(__double2hiint(v)));
+    return __hiloint2double(hi, __double2loint(v));
+}
+
 // GUARD_HI = false: caller guarantees x <= ~700 (correlation entries: x = -s <= 0).
 // No clamp on the low side: for x < -708 the intermediate values are garbage but finite-or-NaN and the
 // final select returns 0; NaN inputs propagate through r.
@@ -51,10 +66,9 @@ __device__ __forceinline__ double exp_fast(double x, const double* __restrict__ 
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = p * r;                                              // expm1(r)
-    const double T = tab[N & (EXP_TAB - 1)];
+    const double T = exp_tab32(N, tab);
     double v = fma(T, p, T);                                // T (1 + expm1 r), one rounding
-    const int hi = __double2hiint(v) + ((N >> 5) << 20);    // * 2^m (result is normal for -708 <= x <= 709)
-    v = __hiloint2double(hi, __double2loint(v));
+    v = exp_scale32(v, N);                                  // * 2^m (result is normal for -708 <= x <= 709)
     v = (x < -708.0) ? 0.0 : v;
     if (GUARD_HI) v = (x > 709.0) ? INFINITY : v;
     return v;
@@ -176,9 +190,9 @@ __device__ __forceinline__ double pow_pos(double x, double p, const PowTables& T
     pe = fma(pe, rr, 0.5);
     pe = fma(pe, rr, 1.0);
     pe = pe * rr;
-    const double Tj = T.e[N & (EXP_TAB - 1)];
+    const double Tj = exp_tab32(N, T.e);
     double v = fma(Tj, pe, Tj);
-    v = __hiloint2double(__double2hiint(v) + ((N >> 5) << 20), __double2loint(v));
+    v = exp_scale32(v, N);
     v = (ph < -708.0) ? 0.0 : v;                   // underflow (also covers tiny / subnormal x)
     v = (ph > 709.0) ? INFINITY : v;
     return (x <= 1.7e308) ? v : x;                 // inf / NaN propagate
@@ -219,9 +233,9 @@ __device__ __forceinline__ double exp_unguarded(double x, const double* __restri
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = p * r;
-    const double T = tab[N & (EXP_TAB - 1)];
+    const double T = exp_tab32(N, tab);
     const double v = fma(T, p, T);
-    return __hiloint2double(__double2hiint(v) + ((N >> 5) << 20), __double2loint(v));
+    return exp_scale32(v, N);
 }
 
 }  // namespace smb
