@@ -176,7 +176,7 @@ int sm_krig_fit(const double* X, const double* y, int n, int k, const double* th
     keep_pool_cached();
     Launches L;
     cudaStream_t st = (cudaStream_t)stream;
-    if (!Mop && nll_uses_flow(n)) {  // weights only, n > 144: dataflow kernel + back-substitution
+    if (!Mop && nll_uses_flow(n)) {  // weights only, n >= 113 (nll_uses_flow): dataflow kernel + back-substitution
         FitOut out{scalars, w, b, rres, nullptr, R};
         SM_TRY(launch_krig_fit_weights(X, y, n, k, theta, p, out, st, &L.n));
         return 0;

@@ -66,7 +66,7 @@ struct FitOut {
     double* R;        // optional [n][n] correlation matrix (may be null)
 };
 size_t fit_tile_doubles(int n);
-// weights-only fit for n > 144 (no Mop): dataflow kernel on one candidate + back-substitution on the kept factor
+// weights-only fit for the sizes of the dataflow kernel (n >= 113 by default; no Mop): dataflow kernel on one candidate + back-substitution on the kept factor
 cudaError_t launch_krig_fit_weights(const double* X, const double* y, int n, int k, const double* theta, const double* p,
                                     FitOut out, cudaStream_t st, long long* launches);
 cudaError_t launch_krig_fit(const double* X, const double* y, int n, int k, const double* theta, const double* p,

@@ -143,7 +143,7 @@ __global__ void corr_matrix_kernel(const double* __restrict__ X, int n, int k, c
     }
 }
 
-// ------------------------------------------------------------------------------------ weights-only fit, n > 144
+// ------------------------------------------------------------------------------------ weights-only fit (sizes the dataflow kernel takes: n >= 113 by default)
 // The dataflow likelihood kernel (krig_nll_flow.cu) runs on ONE candidate with keep_factor set and leaves in the
 // workspace: L (tile (I, K) at (I NT + K) * 64 doubles, operand order, diagonal blocks included) and, in tile row 4 NB,
 // a = L^-1 y (row 0) and b = L^-1 1 (row 1).  This kernel (one CTA) derives mu, sigma^2, rres = a - mu b and

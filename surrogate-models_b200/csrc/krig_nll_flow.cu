@@ -867,9 +867,10 @@ bool nll_uses_flow(int n) {
         return (v && v[0] == '1') || (g && g[0] == '1');
     }();
     const int NT = (n + 7) / 8;
-    // measured crossover against the macro-panel kernel (tools/flow_check.py, k = 8): n = 136: 2.6 vs 3.1 TFLOP/s,
-    // n = 160: 4.1 vs 3.8, n = 256: 6.5 vs 5.9, n = 1024: 16.7 vs 13.5
-    static const int lo = [] { const char* v = getenv("SMB_FLOW_MIN_NT"); return v ? atoi(v) : 18; }();  // tuning
+    // measured crossover against the warp-per-candidate kernel (tools/mid_n_check.py, TFLOP/s small vs dataflow):
+    // n = 96: 5.0 vs 3.8 (k = 2), 3.5 vs 3.7 (k = 8); n = 112: 4.6 vs 3.9; n = 120: 4.9 vs 4.7 (k = 2), 2.4 vs 4.4 (k = 8);
+    // n = 128: 5.2 vs 5.6 (k = 2), 2.6 vs 5.2 (k = 8); n = 144: 5.2 vs 5.5, 2.5 vs 5.0  ->  dataflow kernel from n = 113
+    static const int lo = [] { const char* v = getenv("SMB_FLOW_MIN_NT"); return v ? atoi(v) : 14; }();  // tuning / tests
     return !v1 && NT > lo && (NT + 3) / 4 + 2 <= FLOW_MAXG;
 }
 

@@ -615,6 +615,50 @@ print(json.dumps(dict(b=[float(v) for v in b], c=[float(v) if np.isfinite(v) els
     assert np.median(d) < 1e-11 and np.max(d) < 1e-6
 
 
+def test_warp_per_candidate_kernel_up_to_144_vs_dataflow(K):
+    """113 <= n <= 144 runs on the dataflow kernel by default; SMB_FLOW_MIN_NT=18 keeps those sizes on the
+    warp-per-candidate kernel (its NTM = 16 / 18 instantiations): both must agree, list and grid mode"""
+    import json
+    import subprocess
+    import sys
+    script = r'''
+import json, os, sys
+import numpy as np
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), 'surrogate-models_b200'))
+from mylibs.kriging import Kriging
+from sm_b200 import workloads
+out = {}
+for n, k in ((120, 2), (128, 8), (141, 3), (144, 5)):
+    X, y = workloads.c3_lhs1024(n=n, k=k)
+    e, p = workloads.c3_candidates(300, k)
+    e = np.clip(e, -2.0, 1.0)                      # keep the candidates well conditioned: 1e-10 is meaningful
+    v = Kriging(X * 10, y).likelihood_batch(e, p)
+    out['l%d_%d' % (n, k)] = [float(t) if np.isfinite(t) else None for t in v]
+X, y = workloads.c3_lhs1024(n=136, k=2)
+bv, bi, g = Kriging(X * 10, y).likelihood_grid(6, 3, return_nll=True)
+out['grid'] = [float(t) if np.isfinite(t) else None for t in g.cpu().numpy()]
+out['grid_best'] = int(bi)
+print(json.dumps(out))
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for nt in ('14', '18'):
+        env = dict(os.environ, SMB_FLOW_MIN_NT=nt)
+        r = subprocess.run([sys.executable, '-c', script], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[nt] = json.loads(r.stdout.strip().split('\n')[-1])
+    assert res['14']['grid_best'] == res['18']['grid_best']
+    for key in res['14']:
+        if key == 'grid_best':
+            continue
+        a = np.array([np.nan if v is None else v for v in res['14'][key]])
+        b = np.array([np.nan if v is None else v for v in res['18'][key]])
+        m = np.isfinite(a) & np.isfinite(b)
+        assert m.sum() >= 0.9 * len(a), key
+        d = rel(a[m], b[m])
+        assert np.median(d) < 1e-11 and np.max(d) < 1e-6, (key, float(np.max(d)))
+
+
 def test_lazy_objective_large_n(K):
     """n >= 145: the optimiser objective is one single-candidate launch of the batched kernel and the full fit is
     deferred; value and the state every accessor sees must equal update_param + calc_likelihood"""

@@ -12,7 +12,10 @@ from mylibs.kriging import Kriging  # noqa: E402
 from sm_b200 import _cabi, device, workloads  # noqa: E402
 
 L = _cabi.lib()
-for n, k, C in [(128, 2, 20000), (136, 2, 20000), (144, 2, 20000), (144, 8, 20000), (152, 2, 20000)]:
+SIZES = [(128, 2, 20000), (136, 2, 20000), (144, 2, 20000), (144, 8, 20000), (152, 2, 20000)]
+if len(sys.argv) > 1:  # n,k[;n,k...]
+    SIZES = [(int(t.split(',')[0]), int(t.split(',')[1]), 20000) for t in sys.argv[1].split(';')]
+for n, k, C in SIZES:
     X, y = workloads.c3_lhs1024(n=n, k=k)
     e, p = workloads.c3_candidates(C, k)
     kr = Kriging(X * 10, y)
