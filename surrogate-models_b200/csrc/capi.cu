@@ -101,7 +101,7 @@ int sm_krig_nll_grid(const double* X, const double* y, int n, int k, const doubl
     Launches L;
     const int npad = sm_krig_npad(n);
     DevBuf dtab(st), nll_tmp(st);
-    const bool flow = nll_uses_flow(n);  // n > 128: tile-packed lower-triangle tables for the dataflow kernel
+    const bool flow = nll_uses_flow(n, k);  // tile-packed lower-triangle tables for the dataflow kernel
     if (flow) {
         SM_TRY(dtab.alloc(flow_table_doubles(n) * k * P * 8));
         SM_TRY(launch_dtab_packed(X, n, k, npad, p_axis, P, dtab.as<double>(), st));
@@ -146,7 +146,7 @@ int sm_krig_nll_batch(const double* X, const double* y, int n, int k, const doub
     Launches L;
     const int npad = sm_krig_npad(n);
     DevBuf lg(st), nll_tmp(st);
-    const bool flow = nll_uses_flow(n);  // n > 128: base-2, tile-packed table for the dataflow kernel
+    const bool flow = nll_uses_flow(n, k);  // base-2, tile-packed table for the dataflow kernel
     SM_TRY(lg.alloc((flow ? flow_table_doubles(n) : (size_t)npad * npad) * k * 8));
     if (flow) SM_TRY(launch_log2tab(X, n, k, npad, lg.as<double>(), st));
     else SM_TRY(launch_logtab(X, n, k, npad, lg.as<double>(), st));
@@ -176,7 +176,7 @@ int sm_krig_fit(const double* X, const double* y, int n, int k, const double* th
     keep_pool_cached();
     Launches L;
     cudaStream_t st = (cudaStream_t)stream;
-    if (!Mop && nll_uses_flow(n)) {  // weights only, n >= 113 (nll_uses_flow): dataflow kernel + back-substitution
+    if (!Mop && nll_uses_flow(n, k)) {  // weights only, sizes of the dataflow kernel: that kernel + back-substitution
         FitOut out{scalars, w, b, rres, nullptr, R};
         SM_TRY(launch_krig_fit_weights(X, y, n, k, theta, p, out, st, &L.n));
         return 0;

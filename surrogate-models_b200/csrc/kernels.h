@@ -45,7 +45,7 @@ cudaError_t launch_nll(NllArgs a, int mode, cudaStream_t st, long long* launches
 cudaError_t launch_nll_small(const NllArgs& a, int mode, cudaStream_t st);
 cudaError_t launch_nll_large(NllArgs a, int mode, cudaStream_t st);
 cudaError_t launch_nll_flow(NllArgs a, int mode, cudaStream_t st);
-bool nll_uses_flow(int n);
+bool nll_uses_flow(int n, int k);
 cudaError_t launch_log2tab(const double* X, int n, int k, int npad, double* LG, cudaStream_t st);  // tile-packed, [flow_table_doubles(n)][k]
 cudaError_t launch_dtab_packed(const double* X, int n, int k, int npad, const double* p_axis, int P, double* D, cudaStream_t st);
 size_t flow_table_doubles(int n);  // doubles of ONE tile-packed lower-triangle table

@@ -328,10 +328,10 @@ cudaError_t launch_nll(NllArgs a, int mode, cudaStream_t st, long long* launches
     // SMB_FORCE_GENERIC=1 routes everything through the generic tile engine (cross-check in the tests)
     static const bool force_generic = [] { const char* v = getenv("SMB_FORCE_GENERIC"); return v && v[0] == '1'; }();
     if (!force_generic) {
-        // the table layout was chosen by the caller with nll_uses_flow(n): the same predicate routes the launch
+        // the table layout was chosen by the caller with nll_uses_flow(n, k): the same predicate routes the launch
         // (dataflow kernel above its size threshold, warp-per-candidate kernel below it for k <= 8 (it covers n <= 144), macro-panel
         // kernel for the rest)
-        cudaError_t es = nll_uses_flow(a.n) ? launch_nll_flow(a, mode, st) : launch_nll_small(a, mode, st);
+        cudaError_t es = nll_uses_flow(a.n, a.k) ? launch_nll_flow(a, mode, st) : launch_nll_small(a, mode, st);
         if (es == cudaErrorNotSupported) es = launch_nll_large(a, mode, st);
         if (es != cudaErrorNotSupported) {
             if (launches) *launches += 1;

@@ -860,7 +860,7 @@ static cudaError_t launch_flow_t(NllArgs a, int mode, cudaStream_t st) {
 
 // SMB_LARGE_V1=1 keeps every n > 128 on the barrier-synchronised macro-panel kernel (krig_nll_large.cu; cross-check
 // in the tests); SMB_FLOW_CFG=<LW><ST> (e.g. 43, 82) overrides the warps-per-CTA / ring-depth choice (tuning).
-bool nll_uses_flow(int n) {
+bool nll_uses_flow(int n, int k) {
     static const bool v1 = [] {
         const char* v = getenv("SMB_LARGE_V1");
         const char* g = getenv("SMB_FORCE_GENERIC");
@@ -869,13 +869,16 @@ bool nll_uses_flow(int n) {
     const int NT = (n + 7) / 8;
     // measured crossover against the warp-per-candidate kernel (tools/mid_n_check.py, TFLOP/s small vs dataflow):
     // n = 96: 5.0 vs 3.8 (k = 2), 3.5 vs 3.7 (k = 8); n = 112: 4.6 vs 3.9; n = 120: 4.9 vs 4.7 (k = 2), 2.4 vs 4.4 (k = 8);
-    // n = 128: 5.2 vs 5.6 (k = 2), 2.6 vs 5.2 (k = 8); n = 144: 5.2 vs 5.5, 2.5 vs 5.0  ->  dataflow kernel from n = 113
-    static const int lo = [] { const char* v = getenv("SMB_FLOW_MIN_NT"); return v ? atoi(v) : 14; }();  // tuning / tests
+    // n = 128: 5.2 vs 5.6 (k = 2), 2.6 vs 5.2 (k = 8); n = 144: 5.2 vs 5.5, 2.5 vs 5.0  ->  dataflow kernel from n = 113;
+    // k > 4 (the warp-per-candidate kernel runs its 8-dimension instantiation at half the occupancy): n = 88: 3.4 vs 2.9,
+    // n = 96: 3.4 vs 3.8, n = 104: 2.2 vs 3.0 (k = 8), 2.1 vs 2.8 (k = 5), n = 112: 2.3 vs 3.7  ->  from n = 89
+    static const int lo_env = [] { const char* v = getenv("SMB_FLOW_MIN_NT"); return v ? atoi(v) : -1; }();  // tuning / tests
+    const int lo = lo_env >= 0 ? lo_env : (k > 4 ? 11 : 14);
     return !v1 && NT > lo && (NT + 3) / 4 + 2 <= FLOW_MAXG;
 }
 
 cudaError_t launch_nll_flow(NllArgs a, int mode, cudaStream_t st) {
-    if (!nll_uses_flow(a.n)) return cudaErrorNotSupported;
+    if (!nll_uses_flow(a.n, a.k)) return cudaErrorNotSupported;
     if (a.C <= 0) return cudaSuccess;
     if (mode == 1 && !a.log2tab) return cudaErrorInvalidValue;
     {   // the entry tasks index the tables with 32-bit offsets (doubles)

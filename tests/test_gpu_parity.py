@@ -518,10 +518,11 @@ def test_large_n_and_large_k(K):
     assert check_values(nll16, ref16, cond16, cond_max=1e12) == 6
 
 
-@pytest.mark.parametrize('n,k_', [(145, 3), (353, 2), (361, 5), (377, 16), (500, 3), (520, 1)])
+@pytest.mark.parametrize('n,k_', [(91, 6), (105, 9), (113, 2), (129, 4), (145, 3), (353, 2), (361, 5), (377, 16), (500, 3), (520, 1)])
 def test_dataflow_kernel_ragged_sizes(K, n, k_):
-    """n > 144 runs on the dataflow kernel (krig_nll_flow.cu): tile counts NT = 45, 46, 48, 63, 65 cover every
-    remainder of the 4-tile row groups / macro columns, k = 1 .. 16 every chunking of the entry evaluation"""
+    """n >= 113 (n >= 89 for k > 4) runs on the dataflow kernel (krig_nll_flow.cu): tile counts NT = 12, 14, 15, 17 at
+    its lower end and 45, 46, 48, 63, 65 cover every remainder of the 4-tile row groups / macro columns, k = 1 .. 16
+    every chunking of the entry evaluation"""
     rng = np.random.default_rng(n * 100 + k_)
     X = rng.uniform(0, 10, (n, k_))
     y = np.sin(X.sum(axis=1)) + 0.1 * X[:, 0] ** 2
