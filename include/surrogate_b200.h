@@ -45,6 +45,14 @@ long long sm_b200_launch_count(void);
 /* padded size (multiple of 8) and number of doubles of the packed L^-1 operand tiles for n samples */
 int sm_krig_npad(int n);
 size_t sm_krig_mop_doubles(int n);
+/* Ill-conditioned candidates.  Every likelihood entry point below evaluates a candidate whose smallest Cholesky pivot
+ * (R has a unit diagonal) is <= sm_krig_pivot_tau() a second time in double-double arithmetic on the correlation
+ * matrix formed exactly as the reference forms it (correctly rounded pow / exp; mylibs/kriging.py:70-77), and returns
+ * that value, or +inf if that fp64 matrix is not positive definite (the reference returns LU rounding noise there,
+ * mylibs/kriging.py:79,100).  sm_krig_rescue_stats: candidates re-evaluated / of those finite, summed over the calls on
+ * the current device since the last reset (synchronises the device). */
+double sm_krig_pivot_tau(void);
+int sm_krig_rescue_stats(int64_t* listed, int64_t* finite, int reset);
 
 /* ---- batched likelihood over the reference's grid ------------------------------------------------
  * Replaces LikeliOptimizer.generate_grid (mylibs/likeli_optimizer.py:50-87) calling
@@ -74,7 +82,10 @@ int sm_krig_nll_batch_host(const double* X, const double* y, int n, int k, const
 
 /* ---- single-model fit -------------------------------------------------------------------------------
  * Replaces Kriging.update_param (mylibs/kriging.py:53-63 = _calc_cormat :66-84 + _calc_mu :86-93) and
- * calc_likelihood (:95-116).  scalars[4] = {nll, mu, sigma2, info}; info 1 = not numerically SPD.
+ * calc_likelihood (:95-116).  scalars[4] = {nll, mu, sigma2, info}; info 0 = fp64 fit; 2 = ill-conditioned
+ * (smallest pivot <= sm_krig_pivot_tau()): nll, mu, sigma2, w, b, rres come from the double-double factorisation, Mop
+ * from the fp64 one; 3 = as 2 but the fp64 factorisation failed, Mop is invalid (no MSE); 1 = not positive definite
+ * even in double-double: nll = +inf, the rest NaN.
  * w[n] = R^-1 (y - 1 mu); b[npad] = L^-1 1; rres[npad] = L^-1 (y - 1 mu); Mop[sm_krig_mop_doubles(n)] =
  * L^-1 as packed 8x8 operand tiles (consumed by sm_krig_predict for the MSE); R[n*n] optional (NULL).
  * Mop may be NULL (weights only: no MSE afterwards); for n > 144 the fit then runs on the batched likelihood

@@ -4,6 +4,7 @@ Run in the build container only (the GPU box has no /root/reference):
 
     python oracle/gen_golden.py            # everything except the full 1e6-candidate C2 grids
     python oracle/gen_golden.py --full-c2  # + both full C2 grids (about 15 min each on 8 cores)
+    python oracle/gen_golden.py --only illcond  # ill-conditioned corner of the C2 grids (binary128 / mpmath adjudication)
 
 Test infrastructure; the product never imports this.  Inputs are produced with the reference's own
 generators (mylibs/halton.py, mylibs/structured_sample.py, myutils/samples.py) and stored beside
@@ -159,6 +160,41 @@ def gen_c2_full(procs):
              ref_seconds=secs, ref_procs=procs)
 
 
+def gen_c2_illcond():
+    """The ill-conditioned corner of both full C2 grids (App. E rule iii), tests/golden/c2_illcond_<resp>.npz.
+    S = candidates whose smallest fp64 Cholesky pivot is <= 1e-6 (3 971 of 1e6; R does not depend on y).  For every c in S:
+      ref      the unmodified reference (read from the full run of gen_c2_full when /tmp still holds it, else recomputed)
+      chol     oracle.nll_chol = np.linalg.cholesky (LAPACK potrf) formulation, +inf where potrf fails
+      rounded  binary128 likelihood of the fp64 matrix the reference holds (oracle/quad_oracle.c), +inf = not PD
+      exact    binary128 likelihood from the fp64 inputs (entries in 113 bits too)
+      truth    100-digit mpmath Cholesky for the candidates whose fp64 matrix is not PD (what rule iii adjudicates with)
+    """
+    from oracle import quad, mp_oracle
+    X = np.array(Halton().generate_sample_plan(64, 2, [(0., 10.), (0., 10.)]), dtype=np.float64)
+    e, q = orc.grid_candidates(2, 40, 25)
+    _, mp64 = quad.nll_f64(X, np.zeros(64) + np.arange(64), 10. ** e, q)
+    S = np.flatnonzero(~(mp64 > 1e-6))
+    print('ill-conditioned set:', len(S), flush=True)
+    th = np.zeros_like(e)
+    th[S] = [[10. ** v for v in row] for row in e[S]]  # scalar pow, as the reference forms theta (kriging.py:133-136)
+    for name, f in (('f3d', f_3d), ('fb', fb)):
+        y = np.array([f(x) for x in X])
+        full = os.path.join('/tmp', f'c2_full_{name}_nll.npy')
+        if os.path.exists(full):
+            ref = np.load(full)[S]
+        else:
+            k = Kriging(X, y)
+            ref = np.array([ref_nll(k, np.concatenate([e[c], q[c]])) for c in S])
+        chol = np.array([orc.nll_chol(X, y, th[c], q[c]) for c in S])
+        rounded, rmp = quad.nll_rounded(X, y, th[S], q[S])
+        exact, emp = quad.nll_exact(X, y, th[S], q[S])
+        truth = np.full(len(S), np.nan)
+        for i in np.flatnonzero(~np.isfinite(rounded)):
+            truth[i] = mp_oracle.nll_chol(X, y, th[S[i]], q[S[i]])
+        save(f'c2_illcond_{name}', idx=S, ref=ref, chol=chol, rounded=rounded, rounded_min_pivot=rmp, exact=exact,
+             exact_min_pivot=emp, truth=truth, f64_min_pivot=mp64[S])
+
+
 def gen_c3():
     from scipy.stats import qmc
     X = qmc.LatinHypercube(d=8, seed=0).random(1024)
@@ -277,7 +313,9 @@ if __name__ == '__main__':
     a = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     todo = dict(c1=gen_c1, c2=gen_c2_default, c3=gen_c3, c4=gen_c4, c5=gen_c5, val=gen_validation)
-    if a.full_c2:
+    if a.only == 'illcond':
+        gen_c2_illcond()
+    elif a.full_c2:
         gen_c2_full(a.procs)
     else:
         for name, fn in todo.items():

@@ -41,6 +41,37 @@ def fit(X, y, theta, p):
     return dict(R=R, Rinv=Rinv, mu=mu, s2=s2, nll=nll, w=Rinv * r, one=one)
 
 
+def nll_chol(X, y, theta, p, dps=100):
+    """Likelihood by a Cholesky factorisation in `dps`-digit arithmetic (kriging.py:66-116 in Cholesky form): the
+    adjudicator for candidates beyond binary128 (cond > 1e30).  Returns a float (+inf only if a pivot is <= 0 even
+    at this precision, which does not happen for distinct samples)."""
+    old = mp.mp.dps
+    mp.mp.dps = dps
+    try:
+        n = X.shape[0]
+        R = corr(X, theta, p)
+        L = [[mp.mpf(0)] * n for _ in range(n)]
+        logdet = mp.mpf(0)
+        for j in range(n):
+            d = R[j, j] - sum(L[j][t] * L[j][t] for t in range(j))
+            if d <= 0:
+                return float('inf')
+            ljj = mp.sqrt(d)
+            logdet += mp.log(d)
+            L[j][j] = ljj
+            for i in range(j + 1, n):
+                L[i][j] = (R[i, j] - sum(L[i][t] * L[j][t] for t in range(j))) / ljj
+        a, b = [], []
+        for i in range(n):
+            a.append((mp.mpf(float(y[i])) - sum(L[i][t] * a[t] for t in range(i))) / L[i][i])
+            b.append((1 - sum(L[i][t] * b[t] for t in range(i))) / L[i][i])
+        mu = sum(u * v for u, v in zip(a, b)) / sum(v * v for v in b)
+        s2 = sum((u - mu * v) ** 2 for u, v in zip(a, b)) / n
+        return float(mp.mpf(n) / 2 * mp.log(s2) + logdet / 2)
+    finally:
+        mp.mp.dps = old
+
+
 def predict(X, f, theta, p, Xq):
     n, k = X.shape
     ys, ms = [], []

@@ -86,6 +86,14 @@ const char* sm_b200_error_string(int code) {
     return cudaGetErrorString((cudaError_t)code);
 }
 int sm_krig_npad(int n) { return (n + 7) / 8 * 8; }
+double sm_krig_pivot_tau(void) { return SMB_PIVOT_TAU; }
+int sm_krig_rescue_stats(int64_t* listed, int64_t* finite, int reset) {
+    unsigned long long v[4];
+    SM_TRY(rescue_stats(v, reset));
+    if (listed) *listed = (int64_t)v[0];
+    if (finite) *finite = (int64_t)v[1];
+    return 0;
+}
 size_t sm_krig_mop_doubles(int n) {
     const size_t NT = (size_t)(n + 7) / 8;
     return NT * (NT + 1) / 2 * 64;
@@ -117,7 +125,7 @@ int sm_krig_nll_grid(const double* X, const double* y, int n, int k, const doubl
     NllArgs a{};
     a.X = X; a.y = y; a.n = n; a.k = k; a.npad = npad;
     a.C = c_count; a.c_begin = c_begin;
-    a.theta_axis = theta_axis; a.T = T; a.P = P; a.dtab = dtab.as<double>();
+    a.theta_axis = theta_axis; a.T = T; a.P = P; a.p_axis = p_axis; a.dtab = dtab.as<double>();
     a.nll_out = nll_out;
     // n <= 96, k <= 4 (the warp-per-candidate kernel): product-form entry tables (see egrid_kernel).  The choice depends on the problem shape
     // only, never on the candidate range, so shards of one grid are bit-identical to the full evaluation.

@@ -17,6 +17,7 @@ struct NllArgs {
     // grid mode (MODE 0): theta_axis holds LINEAR theta values (10**exponent done by the caller)
     const double* theta_axis;
     int T, P;
+    const double* p_axis;  // [P] (grid mode; read by the extended-precision rescue pass only)
     const double* dtab;  // [k][P][npad][npad]
     const double* egrid;  // optional [k][P][T][npad][npad]: exp(-theta_axis[t] * dtab) -- product-form entries
     // list mode (MODE 1)
@@ -27,9 +28,20 @@ struct NllArgs {
     // output / scratch
     double* nll_out;    // [C]
     double* workspace;  // tile storage for the global-memory variant
+    double pivot_tau;   // smallest acceptable pivot: set by launch_nll (pivot_tau_for); at or below it the candidate gets +inf
     int keep_factor;    // krig_nll_flow.cu: also store the factor of the diagonal blocks (single-model fit)
     int l2mode;         // krig_nll_flow.cu: bit 0 = evict_first L2 policy on the A strips
 };
+
+// A candidate whose smallest Cholesky pivot is <= SMB_PIVOT_TAU (R has a unit diagonal, so this is relative) gets +inf
+// from every fp64 likelihood kernel and is then re-evaluated in double-double by launch_rescue (krig_rescue.cu).
+// One constant for every engine, so grid / list / fit paths classify a candidate identically.
+#define SMB_PIVOT_TAU 1e-7
+// The double-double pass costs ~35 fp64 operations per multiply-subtract on ONE CTA per candidate (n = 1024: ~0.5 s per
+// candidate), so it runs for n <= rescue_max_n() only (default 256, env SMB_RESCUE_MAX_N); above that the fp64 kernels keep
+// the plain 'pivot > 1e-30' test and a failed factorisation stays +inf.
+int rescue_max_n();
+inline double pivot_tau_for(int n) { return n <= rescue_max_n() ? SMB_PIVOT_TAU : 1e-30; }
 
 struct NllPlan {
     int variant;  // 0: warp per candidate (smem), 1: CTA per candidate (smem), 2: CTA per candidate (global)
@@ -66,6 +78,10 @@ struct FitOut {
     double* R;        // optional [n][n] correlation matrix (may be null)
 };
 size_t fit_tile_doubles(int n);
+// krig_rescue.cu: double-double re-evaluation of every +inf entry of a.nll_out (fit != null: single-model fit, C = 1 --
+// also rewrites mu, sigma2, info, w, b, rres from the double-double factorisation)
+cudaError_t launch_rescue(const NllArgs& a, int mode, cudaStream_t st, long long* launches, const FitOut* fit = nullptr);
+cudaError_t rescue_stats(unsigned long long* out, int reset);
 // weights-only fit for the sizes of the dataflow kernel (n >= 113 by default; no Mop): dataflow kernel on one candidate + back-substitution on the kept factor
 cudaError_t launch_krig_fit_weights(const double* X, const double* y, int n, int k, const double* theta, const double* p,
                                     FitOut out, cudaStream_t st, long long* launches);

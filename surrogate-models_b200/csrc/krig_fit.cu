@@ -59,7 +59,7 @@ size_t fit_tile_doubles(int n) {
 __global__ void __launch_bounds__(256) krig_fit_kernel(const double* __restrict__ X, const double* __restrict__ y,
                                                        int n, int k, const double* __restrict__ theta,
                                                        const double* __restrict__ p, double* __restrict__ tiles,
-                                                       FitOut out) {
+                                                       FitOut out, const double pivot_tau) {
     __shared__ double wscr[8 * 64];
     __shared__ double th_s[KMAX], p_s[KMAX];
     __shared__ double sc[2];
@@ -87,10 +87,13 @@ __global__ void __launch_bounds__(256) krig_fit_kernel(const double* __restrict_
         double mu, s2;
         const double nll = nll_epilogue(rhs_base, n, lane, res.logdet_half, &mu, &s2);
         if (lane == 0) {
-            out.scalars[0] = nll;
+            // ill-conditioned (smallest pivot <= SMB_PIVOT_TAU): +inf + info 2 hand the model to the double-double pass that
+            // launch_krig_fit runs next (nll, mu, sigma^2, w, b, rres from there; L^-1 stays from this factorisation)
+            const bool ill = !(res.min_pivot > pivot_tau);
+            out.scalars[0] = ill ? INFINITY : nll;
             out.scalars[1] = mu;
             out.scalars[2] = s2;
-            out.scalars[3] = 0.0;
+            out.scalars[3] = ill ? 2.0 : 0.0;
             sc[0] = mu;
         }
     }
@@ -143,12 +146,24 @@ __global__ void corr_matrix_kernel(const double* __restrict__ X, int n, int k, c
     }
 }
 
+// scalars[0] == +inf after a fit (not SPD in fp64, or ill-conditioned): the double-double pass re-evaluates the model
+static cudaError_t fit_rescue(const double* X, const double* y, int n, int k, const double* theta, const double* p,
+                              FitOut out, cudaStream_t st, long long* launches) {
+    if (n > rescue_max_n()) return cudaSuccess;
+    NllArgs a{};
+    a.X = X; a.y = y; a.n = n; a.k = k; a.npad = (n + 7) / 8 * 8;
+    a.C = 1; a.c_begin = 0;
+    a.theta = theta; a.p = p;
+    a.nll_out = out.scalars;
+    return launch_rescue(a, 1, st, launches, &out);
+}
+
 // ------------------------------------------------------------------------------------ weights-only fit (sizes the dataflow kernel takes: n >= 113 by default)
 // The dataflow likelihood kernel (krig_nll_flow.cu) runs on ONE candidate with keep_factor set and leaves in the
 // workspace: L (tile (I, K) at (I NT + K) * 64 doubles, operand order, diagonal blocks included) and, in tile row 4 NB,
 // a = L^-1 y (row 0) and b = L^-1 1 (row 1).  This kernel (one CTA) derives mu, sigma^2, rres = a - mu b and
 // back-substitutes L^T w = rres.  nll comes from the likelihood kernel itself (scalars[0]).
-__global__ void __launch_bounds__(256) krig_backsolve_kernel(const double* __restrict__ ws, int n, FitOut out) {
+__global__ void __launch_bounds__(256) krig_backsolve_kernel(const double* __restrict__ ws, int n, FitOut out, const double pivot_tau) {
     extern __shared__ double x_s[];  // [npad]
     __shared__ double red[3][8];
     __shared__ double xj[8];
@@ -165,13 +180,15 @@ __global__ void __launch_bounds__(256) krig_backsolve_kernel(const double* __res
         }
         return;
     }
-    double sab = 0.0, sbb = 0.0;
+    double sab = 0.0, sbb = 0.0, lmin = 1.0;
     for (int j = threadIdx.x; j < n; j += blockDim.x) {
         const double* t = rhs + (size_t)(j >> 3) * 64;
         const double av = t[tile_pos(0, j & 7)], bv = t[tile_pos(1, j & 7)];
         sab = fma(av, bv, sab);
         sbb = fma(bv, bv, sbb);
+        lmin = fmin(lmin, ws[(size_t)(j >> 3) * rowstride + (size_t)(j >> 3) * 64 + tile_pos(j & 7, j & 7)]);  // L_jj
     }
+    const int ill = __syncthreads_or(!(lmin * lmin > pivot_tau));  // smallest pivot L_jj^2 at or below the threshold
     sab = warp_sum(sab);
     sbb = warp_sum(sbb);
     if (lane == 0) {
@@ -203,7 +220,8 @@ __global__ void __launch_bounds__(256) krig_backsolve_kernel(const double* __res
         for (int i = 0; i < 8; ++i) t += red[2][i];
         out.scalars[1] = mu;
         out.scalars[2] = t / n;
-        out.scalars[3] = 0.0;
+        out.scalars[3] = ill ? 2.0 : 0.0;
+        if (ill) out.scalars[0] = INFINITY;  // -> double-double pass (launch_krig_fit_weights), see krig_fit_kernel
     }
     // back-substitution, block row by block row from the bottom
     for (int J = NT - 1; J >= 0; --J) {
@@ -259,11 +277,12 @@ cudaError_t launch_krig_fit_weights(const double* X, const double* y, int n, int
         const size_t smem = (size_t)npad * 8;
         e = cudaFuncSetAttribute(krig_backsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) {
-            krig_backsolve_kernel<<<1, 256, smem, st>>>(ws, n, out);
+            krig_backsolve_kernel<<<1, 256, smem, st>>>(ws, n, out, pivot_tau_for(n));
             e = cudaGetLastError();
         }
     }
     if (launches) *launches += 3;
+    if (e == cudaSuccess) e = fit_rescue(X, y, n, k, theta, p, out, st, launches);
     if (e == cudaSuccess && out.R) {
         int grid = (int)(((size_t)n * n + 255) / 256);
         if (grid > 148 * 8) grid = 148 * 8;
@@ -281,9 +300,10 @@ cudaError_t launch_krig_fit(const double* X, const double* y, int n, int k, cons
     double* tiles = nullptr;
     cudaError_t e = cudaMallocAsync((void**)&tiles, fit_tile_doubles(n) * 8, st);
     if (e != cudaSuccess) return e;
-    krig_fit_kernel<<<1, 256, 0, st>>>(X, y, n, k, theta, p, tiles, out);
+    krig_fit_kernel<<<1, 256, 0, st>>>(X, y, n, k, theta, p, tiles, out, pivot_tau_for(n));
     e = cudaGetLastError();
     if (launches) *launches += 1;
+    if (e == cudaSuccess) e = fit_rescue(X, y, n, k, theta, p, out, st, launches);
     if (e == cudaSuccess && out.R) {
         int grid = (int)(((size_t)n * n + 255) / 256);
         if (grid > 148 * 8) grid = 148 * 8;

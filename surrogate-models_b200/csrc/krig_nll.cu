@@ -184,7 +184,7 @@ krig_nll_kernel(const NllArgs a) {
         }
         if (ewid == 0) {
             double nll = INFINITY;
-            if (res.ok) {
+            if (res.ok && res.min_pivot > a.pivot_tau) {  // otherwise +inf: re-evaluated in double-double (krig_rescue.cu)
                 const double* rhs_row = tiles + (size_t)NT * (NT + 1) / 2 * 64;
                 nll = nll_epilogue(rhs_row, a.n, lane, res.logdet_half, nullptr, nullptr);
             }
@@ -321,7 +321,18 @@ static cudaError_t launch_variant(const NllArgs& a, int mode, int grid, int thre
 }
 
 // Runs the likelihood kernel over a.C candidates; tables must already be in a.dtab / a.logtab.
+static cudaError_t launch_nll_fp64(NllArgs a, int mode, cudaStream_t st, long long* launches);
+
+// fp64 kernel of the problem's size class, then the double-double pass over the candidates it flagged with +inf
 cudaError_t launch_nll(NllArgs a, int mode, cudaStream_t st, long long* launches) {
+    a.pivot_tau = pivot_tau_for(a.n);
+    cudaError_t e = launch_nll_fp64(a, mode, st, launches);
+    if (e != cudaSuccess || a.C <= 0 || a.n > rescue_max_n()) return e;
+    a.npad = plan_nll(a.n).npad;
+    return launch_rescue(a, mode, st, launches);
+}
+
+static cudaError_t launch_nll_fp64(NllArgs a, int mode, cudaStream_t st, long long* launches) {
     const NllPlan pl = plan_nll(a.n);
     a.npad = pl.npad;
     if (a.C <= 0) return cudaSuccess;

@@ -440,7 +440,7 @@ __device__ __forceinline__ void flow_task_u(FlowCtl& S, const NllArgs& a, double
 // ---------------------------------------------------------------------------------------------- task P(b)
 // 8 x 8 Cholesky + inverse of one diagonal tile.  In: the tile in accumulator layout (c0, c1).  Out: W = L^-1 in
 // operand order in `wt` (the B operand of the panel products and of the U solves), the product of the 8 pivots in
-// `tp`, optionally L itself in `lt` (operand order, single-model fit); false on a pivot <= 1e-30 / NaN.
+// `tp`, optionally L itself in `lt` (operand order, single-model fit); false on a pivot <= SMB_PIVOT_TAU / NaN.
 // Same scheme as the warp-per-candidate kernel (krig_nll_small.cu, diag_factor): the pivot travels by ONE shuffle from
 // the register that holds the updated diagonal element, everything else of a step is broadcast through the
 // column-major scratch `ts` and is off the serial chain; the rank-1 update of W runs one step late so that one
@@ -448,7 +448,7 @@ __device__ __forceinline__ void flow_task_u(FlowCtl& S, const NllArgs& a, double
 // replaces issued ~35 per pivot, and on a scheduler shared with DMMA-issuing warps every one of them queues behind
 // 16-cycle tensor instructions (the block factorisation is the serial chain of the whole candidate).
 __device__ __forceinline__ bool flow_diag_factor(double c0, double c1, double* __restrict__ ts, double* __restrict__ wt,
-                                                 double* __restrict__ lt, double& tp, const int lane) {
+                                                 double* __restrict__ lt, double& tp, const int lane, const double tau) {
     const int r = lane >> 2, q = lane & 3;
     const int p0 = 2 * ((2 * q) & 3) + (q >> 1);  // tile_pos(i, 2q) - 8 i; column 2q + 1 sits 2 doubles later
     bool ok = true;
@@ -468,7 +468,7 @@ __device__ __forceinline__ bool flow_diag_factor(double c0, double c1, double* _
         }
         const double vr = ts[j * 8 + r];
         const double2 vc = *reinterpret_cast<const double2*>(ts + j * 8 + 2 * q);
-        ok = ok && (d > 1e-30);  // also false for NaN
+        ok = ok && (d > tau);  // also false for NaN; such candidates go to the double-double pass
         tp *= d;
         // 1/d and 1/sqrt(d) from one seed y ~ d^-1/2, e = 1 - d y^2:  1/d = y^2 (1 + e + e^2),  d^-1/2 = y (1 + e/2 + 3 e^2/8)
         const double y = rsqrt_seed(d);
@@ -544,6 +544,9 @@ __device__ __forceinline__ bool flow_task_p(FlowCtl& S, const NllArgs& a, double
     if (b >= 2) wait_ge(&S.coldone[b - 2], G.NB - (b - 2));  // the W slot's previous users are done
     FPH_MARK(5);
     double* const Wb = S.W[b & 1];
+    // single-model fit (keep_factor): the weights are wanted for every factorisable matrix; the ill-conditioned ones are
+    // classified from the kept factor afterwards (krig_backsolve_kernel)
+    const double tau = a.keep_factor ? 1e-30 : a.pivot_tau;
     pm = 1.0;
     pe = 0;
 #pragma unroll 1
@@ -551,7 +554,7 @@ __device__ __forceinline__ bool flow_task_p(FlowCtl& S, const NllArgs& a, double
         const int tt = t * (t + 1) / 2 + t;
         double c0, c1, tp;
         ld_acc(scr + tt * 64, lane, c0, c1);  // own positions: no hazard with the updates of the previous step
-        if (!flow_diag_factor(c0, c1, ts, Wb + tt * 64, lt, tp, lane)) return false;
+        if (!flow_diag_factor(c0, c1, ts, Wb + tt * 64, lt, tp, lane, tau)) return false;
         {   // tp is a positive normal number (8 pivots in (1e-30, ~1]): split off its exponent
             const int hi = __double2hiint(tp);
             pe += (hi >> 20) - 1023;

@@ -101,7 +101,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 // same 8x8 factor + inverse as the small kernel (shared-memory broadcast), unswizzled W output
 __device__ __forceinline__ bool diag_factor_plain(double c0, double c1, double* __restrict__ ts, double* __restrict__ wt,
-                                                  double& tp, int lane) {
+                                                  double& tp, int lane, const double tau) {
     const int r = lane >> 2, q = lane & 3;
     bool ok = true;
     double w0 = (r == 2 * q) ? 1.0 : 0.0, w1 = (r == 2 * q + 1) ? 1.0 : 0.0;
@@ -123,7 +123,7 @@ __device__ __forceinline__ bool diag_factor_plain(double c0, double c1, double* 
         const double d = ts[j * 8 + j];
         const double vr = ts[j * 8 + r];
         const double2 vc = *reinterpret_cast<const double2*>(ts + j * 8 + 2 * q);
-        ok = ok && (d > 0.0);
+        ok = ok && (d > tau);
         tp *= d;
         const double inv = rsqrt(d);
         const double t = vr * (inv * inv);
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(LW * 32, 16 / LW) krig_nll_large_kernel(const 
                 // diagonal tile: every warp factors it redundantly (no broadcast of W needed)
                 double c0, c1, tp;
                 ld_acc(tile_ptr(J, J), lane, c0, c1);
-                ok = diag_factor_plain(c0, c1, scr[wid] + 64, scr[wid], tp, lane) && ok;
+                ok = diag_factor_plain(c0, c1, scr[wid] + 64, scr[wid], tp, lane, a.pivot_tau) && ok;
                 if (wid == 0 && lane == (J & 7)) prod *= tp;
                 if (wid == 0 && (J & 7) == 7) {  // fold before the product of up to 64 pivots can underflow
                     logacc += log(prod);

@@ -117,7 +117,7 @@ __device__ __forceinline__ void eval_entry(const SmallParams<KD>& P, const doubl
 //                  the rank-1 update of the rows below runs one step late so ONE __syncwarp per step suffices.
 // Entries outside the lower triangle pick up meaningless (finite) updates and are never read.
 __device__ __forceinline__ bool diag_factor(double c0, double c1, double* __restrict__ ts, double* __restrict__ wt,
-                                            double& tp, int lane) {
+                                            double& tp, int lane, const double tau) {
     const int r = lane >> 2, q = lane & 3;
     const int s = (r >> 1) & 1;
     bool ok = true;
@@ -146,7 +146,7 @@ __device__ __forceinline__ bool diag_factor(double c0, double c1, double* __rest
         const double2 vc = *reinterpret_cast<const double2*>(ts + j * 8 + 2 * q);
         // 1/d and 1/sqrt(d) from one fp32 seed y ~ d^-1/2 (rel. error e/2, e = 1 - d y^2 ~ 1e-7):
         //   1/d = y^2 (1 + e + e^2) + O(e^3),   1/sqrt(d) = y (1 + e/2 + 3 e^2 / 8) + O(e^3)
-        ok = ok && (d > 1e-36);  // below that R is numerically singular (and the fp32 seed would underflow)
+        ok = ok && (d > tau);  // at or below: +inf here, re-evaluated in double-double (krig_rescue.cu); NaN fails too
         tp *= d;
         const double y = rsqrt_seed(d);
         const double y2 = y * y;
@@ -414,7 +414,7 @@ krig_nll_small_kernel(const NllArgs a) {
             SPH_MARK(3);
             // ------------------------------------------------------------ D: diagonal tile
             double tp;
-            ok = diag_factor(dc0, dc1, dscr, wscr, tp, lane) && ok;  // ends with __syncwarp
+            ok = diag_factor(dc0, dc1, dscr, wscr, tp, lane, a.pivot_tau) && ok;  // ends with __syncwarp
             if (!ok) break;  // warp-uniform
             if (lane == J) prod = tp;  // NT <= 8: lane J keeps the pivot product of tile J
             SPH_MARK(4);

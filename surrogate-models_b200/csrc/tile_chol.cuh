@@ -35,6 +35,7 @@ __device__ __forceinline__ void engine_sync() {
 struct CholResult {
     bool ok;             // false: a pivot was <= 0 or NaN (not numerically SPD)
     double logdet_half;  // sum_i log L_ii   (= 0.5 ln det)
+    double min_pivot;    // smallest elimination pivot d_j = L_jj^2 (the likelihood callers compare it with SMB_PIVOT_TAU)
 };
 
 // GI = tiles of one block column a warp keeps in flight (independent DMMA accumulator chains).
@@ -56,7 +57,7 @@ __device__ __forceinline__ CholResult tile_cholesky(double* __restrict__ tiles, 
                         : rhs_base + ((size_t)(I - NT) * NT + K) * 64;
     };
     auto kstart = [&](int I) -> int { return (TRI0 >= 0 && I >= NT + TRI0) ? I - NT - TRI0 : 0; };
-    double prod = 1.0, logacc = 0.0;
+    double prod = 1.0, logacc = 0.0, dmin = 1.0;
     bool ok = true;
 
     for (int J = 0; J < NT; ++J) {
@@ -110,6 +111,7 @@ __device__ __forceinline__ CholResult tile_cholesky(double* __restrict__ tiles, 
             const double v = (j & 1) ? c1 : c0;
             const double d = __shfl_sync(0xffffffffu, v, 4 * j + (j >> 1));
             if (!(d > 0.0)) ok = false;  // warp-uniform (d is a broadcast); NaN lands here too
+            dmin = fmin(dmin, d);
             const double inv = rsqrt(d);
             if (lane == j) prod *= d;
             const double lr = __shfl_sync(0xffffffffu, v, (lane & ~3) | (j >> 1)) * inv;   // L[r][j]
@@ -153,6 +155,7 @@ __device__ __forceinline__ CholResult tile_cholesky(double* __restrict__ tiles, 
     }
     CholResult res;
     res.ok = ok;
+    res.min_pivot = dmin;
     logacc += log(prod);
     // lanes 0..7 hold the partial pivot logs (sum of ln d = 2 sum ln L_ii)
     double s = (lane < 8) ? logacc : 0.0;

@@ -74,7 +74,9 @@ class Kriging:
                                   device.ptr(f['rres']), device.ptr(f['Mop']), device.ptr(f['R']),
                                   device.stream()))
         sc = f['scalars'].cpu().numpy()  # synchronises
-        f['nll'], f['mu'], f['sigma2'], f['ok'] = float(sc[0]), float(sc[1]), float(sc[2]), sc[3] == 0.0
+        # info (sc[3]): 0 fp64 fit, 2 / 3 ill-conditioned -> values from the double-double factorisation (3: no MSE operand),
+        # 1 not positive definite
+        f['nll'], f['mu'], f['sigma2'], f['ok'], f['info'] = float(sc[0]), float(sc[1]), float(sc[2]), sc[3] != 1.0, int(sc[3])
         return f
 
     def _ensure_mse_state(self):
@@ -246,47 +248,75 @@ class Kriging:
     def optimize(self, init_guess=None, opti_algo='grid', record_data=False):
         """
         runs automatic optimization of thetas and ps (reference: kriging.py:154-204)
-        :param init_guess: list of input values for an initial guess
-        :param opti_algo: 'grid' (LikeliOptimizer: batched GPU grid + SLSQP) or 'basin' (scipy basin-hopping)
+        :param init_guess: list of input values for an initial guess ('basin' only)
+        :param opti_algo: 'grid' (LikeliOptimizer: batched GPU grid + SLSQP), 'basin' (scipy basin-hopping with the
+                          reference's step / accept rules) or -- additive -- 'restarts' (seeded random starts, evaluated
+                          as one batch, SLSQP from the best few; the deterministic replacement of 'basin')
         :param record_data: record every evaluated parameter vector in self.records
         """
         timer = TimeTrack('optiTimer')
-        self.records = None
-        if record_data:
-            self.records = []
-        if 'basin' in opti_algo:
-            if init_guess is None:
-                init_guess = []
-                for t in self._theta:
-                    init_guess.append(t)
-                for p in self._p:
-                    init_guess.append(p)
-            bnds = []
-            for i in range(0, self._k):
-                bnds.append((-5., +5.))
-            for i in range(0, self._k):
-                bnds.append((1., 2.))
-            bounds = BasinHoppingBounds(xmax=list(zip(*bnds))[1], xmin=list(zip(*bnds))[0])
-            step = BasinHoppingStep()
-            minimizer_kwargs = dict(method='SLSQP', bounds=bnds, options={'disp': False, 'maxiter': 5e3}, tol=1e-4)
-            timer.tic()
-            res = basinhopping(self._calc_likelihood_opti_exp, init_guess, minimizer_kwargs=minimizer_kwargs,
-                               accept_test=bounds, take_step=step, niter=1000, niter_success=100)
-            timer.toc(print_it=True)
-        elif 'grid' in opti_algo:
-            skipper = LikeliOptimizer(debug=True)
-            timer.tic()
-            res = skipper.find(self._calc_likelihood_opti_exp, self._k)
-            timer.toc(print_it=True)
+        self.records = [] if record_data else None
+        searches = (('basin', lambda: self._search_basin(init_guess)),
+                    ('grid', lambda: LikeliOptimizer(debug=True).find(self._calc_likelihood_opti_exp, self._k)),
+                    ('restarts', self._search_restarts))
+        for key, search in searches:      # substring match in the reference's order (kriging.py:166,191)
+            if key in opti_algo:
+                timer.tic()
+                res = search()
+                timer.toc(print_it=True)
+                break
         else:
             raise Exception('ERROR: unknown optimizer selected')
-        exps = res.x[0:self._k]
-        thetas = []
-        for e in exps:
-            thetas.append(10. ** e)
         if record_data:
             print('Kriging Likelihood optimization evaluations: {:d}'.format(len(self.records)))
-        self.update_param(thetas, res.x[self._k:])
+        x = res.x
+        self.update_param([10. ** e for e in x[0:self._k]], x[self._k:])
+
+    def _search_box(self):
+        """[-5, 5]^k for log10(theta), [1, 2]^k for p (kriging.py:173-177)"""
+        return [(-5., +5.)] * self._k + [(1., 2.)] * self._k
+
+    def _search_basin(self, init_guess):
+        """scipy basin-hopping exactly as the reference configures it (kriging.py:166-190): 1000 hops, stop after 100
+        without improvement, SLSQP inner minimiser, BasinHoppingStep proposals filtered by BasinHoppingBounds.  Draws
+        from numpy's global generator like the reference (seed it with np.random.seed for a reproducible run)."""
+        if init_guess is None:
+            init_guess = list(self._theta) + list(self._p)
+        box = self._search_box()
+        lo, hi = zip(*box)
+        inner = dict(method='SLSQP', bounds=box, options={'disp': False, 'maxiter': 5e3}, tol=1e-4)
+        return basinhopping(self._calc_likelihood_opti_exp, init_guess, minimizer_kwargs=inner,
+                            accept_test=BasinHoppingBounds(xmax=hi, xmin=lo), take_step=BasinHoppingStep(),
+                            niter=1000, niter_success=100)
+
+    restart_seed = 0       # 'restarts': generator seed, number of random starts per batch and of SLSQP refinements
+    restart_points = 4096
+    restart_refine = 4
+
+    def _search_restarts(self):
+        """Deterministic global search: `restart_points` uniformly random parameter vectors in
+        the search box are evaluated in ONE likelihood_batch launch, SLSQP refines the best `restart_refine` of them,
+        the best end point wins (ties: the earlier start)."""
+        rng = np.random.default_rng(self.restart_seed)
+        lo, hi = (np.array(v) for v in zip(*self._search_box()))
+        starts = rng.uniform(lo, hi, (self.restart_points, 2 * self._k))
+        nll = self.likelihood_batch(starts[:, :self._k], starts[:, self._k:])
+        if self.records is not None:
+            self.records.extend(starts)
+        order = np.argsort(np.where(np.isfinite(nll), nll, np.inf), kind='stable')[:self.restart_refine]
+        best = None
+        for i in order:
+            res = minimize(self._calc_likelihood_opti_exp, starts[i], method='SLSQP', tol=1e-8,
+                           options={'disp': False, 'maxiter': 5e3}, bounds=self._search_box())
+            if best is None or res.fun < best.fun:
+                best = res
+        return best
+
+    def grid_top(self, theta_sections=8, p_sections=5, m=4):
+        """parameter vectors of the m best (finite) grid candidates, best first, ties by index (for multi-start SLSQP)"""
+        _, _, nll = self.grid_search(theta_sections, p_sections, return_nll=True)
+        order = np.argsort(np.where(np.isfinite(nll), nll, np.inf), kind='stable')[:m]
+        return [grid_param(self._k, theta_sections, p_sections, int(c)) for c in order if np.isfinite(nll[c])]
 
     def predict(self, x_pred):
         """
@@ -500,12 +530,11 @@ def grid_param(k, theta_sections, p_sections, c):
     return param
 
 
-"""
-helper classes for basin hopping (reference: kriging.py:336-365)
-"""
+# ---- helper objects for scipy.optimize.basinhopping (reference: kriging.py:336-365) -----------------------------------
 
 
 class BasinHoppingBounds(object):
+    """accept_test: a hop is kept only if every coordinate lies inside [xmin, xmax]"""
 
     def __init__(self, xmax=[5., 5., 2., 2.], xmin=[-5., -5., 1., 1.]):
         self.xmax = np.array(xmax)
@@ -513,22 +542,19 @@ class BasinHoppingBounds(object):
 
     def __call__(self, **kwargs):
         x = kwargs["x_new"]
-        tmax = bool(np.all(x <= self.xmax))
-        tmin = bool(np.all(x >= self.xmin))
-        return tmax and tmin
+        return bool(np.all(x <= self.xmax) and np.all(x >= self.xmin))
 
 
 class BasinHoppingStep(object):
+    """take_step: a completely fresh random point.  Quirk of the reference kept on purpose (kriging.py:357-365,
+    SURVEY.md App. A.8): the first half of x is drawn as 10**U(-5, 5) although the objective reads those slots as
+    EXPONENTS, so BasinHoppingBounds throws most proposals away; the second half is p ~ U(1, 2)."""
 
     def __init__(self, stepsize=1.):
         self.stepsize = stepsize
 
     def __call__(self, x):
-        # the reference writes 10**U(-5,5) into the theta slots although the objective reads them as
-        # exponents (kriging.py:357-365); kept as is -- the bounds test rejects most such proposals
-        for i in range(0, len(x)):
-            if i < len(x) / 2:
-                x[i] = 10**np.random.uniform(-5, 5)
-            else:
-                x[i] = np.random.uniform(1., 2)
+        half = len(x) / 2
+        for slot in range(len(x)):
+            x[slot] = 10 ** np.random.uniform(-5, 5) if slot < half else np.random.uniform(1., 2)
         return x

@@ -1,26 +1,34 @@
-"""Wall-clock timer with the interface of the reference's myutils/time_track.py:18-38
-(Kriging.optimize prints `optiTimer: ... s` through it, mylibs/kriging.py:162,193-195)."""
-from timeit import default_timer as timer
+"""Stop-watch used by Kriging.optimize for its `optiTimer: ... s` line.
+
+Interface of the reference's myutils/time_track.py:18-38 (``tic`` / ``toc(print_it)`` / ``print_time`` /
+``get_time``; constructing the object starts the clock), implemented on ``time.perf_counter``.
+"""
+import time
 
 
 class TimeTrack:
 
     def __init__(self, name='defaultTimer'):
         self._name = name
-        self._stop = None
-        self._start = timer()
+        self._t0 = time.perf_counter()
+        self._lap = None  # seconds measured by the last toc()
 
     def tic(self):
-        self._start = timer()
+        """(re)start the clock"""
+        self._t0 = time.perf_counter()
+        self._lap = None
 
     def toc(self, print_it=False):
-        self._stop = timer()
+        """seconds since construction / the last tic(); optionally prints them like the reference does"""
+        self._lap = time.perf_counter() - self._t0
         if print_it:
             self.print_time()
-        return self._stop - self._start
+        return self._lap
 
     def print_time(self):
-        print(self._name + ': ' + str(self._stop - self._start) + ' s')
+        lap = self._lap if self._lap is not None else self.get_time()
+        print('{}: {} s'.format(self._name, lap))
 
     def get_time(self):
-        return timer() - self._start
+        """running time without stopping"""
+        return time.perf_counter() - self._t0

@@ -23,6 +23,8 @@ SIGNATURES = {
     'sm_b200_launch_count': (ctypes.c_longlong, []),
     'sm_krig_npad': (_i, [_i]),
     'sm_krig_mop_doubles': (ctypes.c_size_t, [_i]),
+    'sm_krig_pivot_tau': (_d, []),
+    'sm_krig_rescue_stats': (_i, [_vp, _vp, _i]),
     'sm_krig_nll_grid': (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _i, _i64, _i64, _vp, _vp, _vp, _vp]),
     'sm_krig_nll_grid_host': (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _i, _i64, _i64, _vp, _vp, _vp]),
     'sm_krig_nll_batch': (_i, [_vp, _vp, _i, _i, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
@@ -76,6 +78,13 @@ def hptr(a):
 
 def f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def rescue_stats(reset=False):
+    """(candidates re-evaluated in double-double, of those finite) since the last reset on the current device."""
+    a, b = ctypes.c_int64(0), ctypes.c_int64(0)
+    check(lib().sm_krig_rescue_stats(ctypes.byref(a), ctypes.byref(b), 1 if reset else 0))
+    return int(a.value), int(b.value)
 
 
 def launch_count():

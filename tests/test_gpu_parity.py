@@ -152,34 +152,54 @@ def test_c2_full_grid_1e6(gold, K, resp):
     X, y = workloads.c2_halton64(resp)
     assert np.array_equal(X, g['X'])
     k = K(X, y)
+    _cabi.rescue_stats(reset=True)
     bv, bi, nll_d = k.likelihood_grid(40, 25)
+    stats = _cabi.rescue_stats()
     nll = nll_d.cpu().numpy()
     assert nll.shape == (1000000,)
     # values on the stratified subset + top-256 of the reference, conditioning-aware
     assert check_values(nll[g['idx']], g['nll'], g['cond']) > 5000
     # first-minimum semantics
     assert bi == orc.first_min_vec(nll) and bv == nll[bi]
-    # index parity over the numerically-SPD set: mask what the GPU's Cholesky rejects,
-    # then the reference's first minimum must be the GPU's
-    spd = np.isfinite(nll)
+    # ---- index parity, UNMASKED where the reference's own optimum is genuine
+    ic = np.load(os.path.join(GOLD, f'c2_illcond_{resp}.npz'))
+    S, gS = ic['idx'], nll[ic['idx']]
+    listed, finite = stats
+    print(f'[{resp}] double-double pass: {listed} candidates re-evaluated, {finite} finite; '
+          f'potrf-finite in the ill-conditioned set: {int(np.isfinite(ic["chol"]).sum())}; '
+          f'GPU-finite: {int(np.isfinite(gS).sum())}; potrf finite & GPU inf: '
+          f'{int((np.isfinite(ic["chol"]) & ~np.isfinite(gS)).sum())}')
+    # (ii) the GPU accepts every candidate LAPACK's Cholesky accepts
+    assert not (np.isfinite(ic['chol']) & ~np.isfinite(gS)).any()
+    # accepted <=> the fp64 matrix the reference holds is positive definite (decided in binary128 by the oracle)
+    deep = ic['f64_min_pivot'] <= 0.5 * _cabi.lib().sm_krig_pivot_tau()      # certainly re-evaluated on the GPU
+    assert np.array_equal(np.isfinite(gS[deep]), np.isfinite(ic['rounded'][deep]))
+    # ... and the value is that matrix's exact likelihood (entries differ from glibc's in ~3e-4 of the cases by one
+    # ulp, which moves the value by ~1e-16 / pivot)
+    m = deep & np.isfinite(ic['rounded'])
+    err = np.abs(gS[m] - ic['rounded'][m])
+    assert np.all(err <= 1e-9 * np.maximum(1, np.abs(ic['rounded'][m])) + 1e-13 / ic['rounded_min_pivot'][m]), err.max()
+    # rule 3: where fp64 conditioning defeats the reference, the GPU is at least as close to the exact value
+    t = ic['exact'][m]
+    ok3 = np.abs(gS[m] - t) <= np.maximum(1e-9 * np.maximum(1, np.abs(t)), 1.5 * np.abs(ic['ref'][m] - t))
+    print(f"[{resp}] rule 3: GPU within max(1e-9, 1.5 x reference error) of the exact value for {ok3.mean():.1%} of {int(m.sum())} candidates")
+    assert ok3.mean() > 0.8, ok3.mean()
+    # (iii) every candidate the GPU rejects although the reference scores it below the GPU's optimum is an artefact
+    # of the reference's LU noise: its true likelihood (100-digit mpmath fixture) is above the GPU's optimum
+    under = np.isfinite(ic['ref']) & (ic['ref'] < bv) & ~np.isfinite(gS)
+    assert np.all(ic['truth'][under] > bv), (S[under], ic['truth'][under])
     ref_sub = dict(zip(g['idx'].tolist(), g['nll'].tolist()))
-    top = [int(c) for c in g['top_idx'] if spd[c]]
-    ref_masked_argmin = min(top, key=lambda c: (ref_sub[c], c))
-    assert bi == ref_masked_argmin
+    undercut = {int(c) for c in g['top_idx'] if ref_sub[int(c)] < bv and int(c) != bi}   # from the reference's full run
+    assert undercut <= set(S[under].tolist()) | ({int(g['argmin'])} if resp == 'f3d' else set())
     if resp == 'fb':
-        assert bi == 960447                                           # App. E; cond 9.9e5
+        assert int(g['argmin']) == 998402 and 998402 in S[under]             # the reference's artefact optimum (truth +1302)
+        assert bi == 960447                                                   # App. E; cond 9.9e5
         assert rel(bv, -41.300450780839526) < 1e-9
     else:
-        # the literal config: the reference's optimum 998813 sits at cond 5e17 (reference -268.12, exact
-        # -264.66) where R is numerically singular in fp64 -- whether a Cholesky survives there is a coin
-        # flip of rounding order.  Contract: the GPU's argmin is the reference's argmin over the candidates
-        # the GPU accepts, and everything it rejects ahead of it is beyond cond 1e12.
-        ahead = [int(c) for c in g['top_idx'] if ref_sub[int(c)] < ref_sub[bi]]
-        cond_of = dict(zip(g['idx'].tolist(), g['cond'].tolist()))
-        assert all((not spd[c]) and cond_of[c] > 1e12 for c in ahead)
-    # every reference-finite candidate rejected by the GPU is hopelessly ill-conditioned
-    both = np.isin(g['idx'], np.flatnonzero(~spd)) & np.isfinite(g['nll'])
-    assert np.all(g['cond'][both] > 1e12)
+        # the literal config: same index as the reference, unmasked.  cond(R) = 5e17 there: reference -268.12, LAPACK
+        # Cholesky -266.14, exact (mpmath) -264.66, exact likelihood of the fp64 matrix -265.47 (what the GPU returns)
+        assert bi == int(g['argmin']) == 998813
+        assert abs(bv - (-265.47)) < 0.05
     # sharded evaluation (what ranks do) reproduces the same vector and argmin, bit for bit
     half = 500000
     b0, i0, n0 = k.likelihood_grid(40, 25, 0, half)
@@ -187,6 +207,88 @@ def test_c2_full_grid_1e6(gold, K, resp):
     assert np.array_equal(np.concatenate([n0.cpu().numpy(), n1.cpu().numpy()]), nll, equal_nan=True)
     from sm_b200 import dist
     assert dist.first_min_pairs([b0, b1], [i0, i1]) == (bv, bi)
+
+
+def host_dd_likelihood(tmp_path, X, y, theta, p):
+    """the GPU's double-double pass, restated serially on the host from the same header (tools/dd_check.cpp)"""
+    import ctypes
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = str(tmp_path / 'libdd_check.so')
+    subprocess.run(['g++', '-O2', '-ffp-contract=off', '-fopenmp', '-shared', '-fPIC',
+                    os.path.join(root, 'tools', 'dd_check.cpp'), '-o', so], check=True)
+    lib = ctypes.CDLL(so)
+    dp = ctypes.POINTER(ctypes.c_double)
+    arr = [np.ascontiguousarray(a, dtype=np.float64) for a in (X, y, theta, p)]
+    out, mpv = np.empty(arr[2].shape[0]), np.empty(arr[2].shape[0])
+    lib.dd_nll_batch(*[a.ctypes.data_as(dp) for a in arr[:2]], X.shape[0], X.shape[1], *[a.ctypes.data_as(dp) for a in arr[2:]],
+                     ctypes.c_long(arr[2].shape[0]), out.ctypes.data_as(dp), mpv.ctypes.data_as(dp))
+    return out
+
+
+def test_ill_conditioned_candidates_same_on_every_path(gold, K, tmp_path):
+    """one pivot threshold for every engine.  Grid mode, list mode and the single-model fit must classify
+    (finite / +inf) and value the near-singular candidates of the kriging_r3 default grid identically -- they all hand
+    them to the same double-double pass -- and the accepted set is what binary128 says is positive definite."""
+    from oracle import quad
+    g = gold('c5_kriging_r3')
+    X, y = g['X'], g['y']
+    k = K(X, y)
+    _cabi.rescue_stats(reset=True)
+    _, _, nll_grid = k.grid_search(8, 5, return_nll=True)
+    listed, finite = _cabi.rescue_stats()
+    e, q = orc.grid_candidates(2, 8, 5)
+    th = np.array([[10. ** v for v in row] for row in e])              # scalar pow, as the grid path forms theta
+    nll_list = k._likelihood_list(th, q)[0]
+    rounded, rmp = quad.nll_rounded(X, y, th, q)
+    _, f64mp = quad.nll_f64(X, y, th, q)
+    deep = f64mp <= 0.5 * _cabi.lib().sm_krig_pivot_tau()
+    assert listed >= deep.sum() > 50 and finite > 0
+    assert np.array_equal(nll_grid[deep], nll_list[deep], equal_nan=True)       # bit-identical: same kernel, same inputs
+    assert np.array_equal(np.isfinite(nll_grid[deep]), np.isfinite(rounded[deep]))
+    m = deep & np.isfinite(rounded)
+    assert np.all(np.abs(nll_grid[m] - rounded[m]) <= 1e-9 * np.maximum(1, np.abs(rounded[m])) + 1e-13 / rmp[m])
+    # ... and bit for bit what the same double-double source computes on the host (tools/dd_check.cpp builds csrc/dd.cuh
+    # with g++); only ln() differs (CUDA vs glibc, 1 ulp)
+    host_nll = host_dd_likelihood(tmp_path, X, y, th[deep], q[deep])
+    assert np.array_equal(np.isfinite(host_nll), np.isfinite(nll_grid[deep]))
+    fin = np.isfinite(host_nll)
+    assert np.max(np.abs(host_nll[fin] - nll_grid[deep][fin]) / np.maximum(1, np.abs(host_nll[fin]))) < 1e-12
+    for c in np.flatnonzero(deep)[::7]:
+        k.update_param(th[c], q[c])
+        v = k.calc_likelihood()
+        assert (v == nll_grid[c]) or (np.isinf(v) and np.isinf(nll_grid[c])), (c, v, nll_grid[c])
+        assert k._fit['info'] in (1, 2, 3)
+        if np.isfinite(v):   # the weights come from the double-double factorisation; psi(x) is still fp64, so the
+            # interpolation error is ~cond * eps (cond up to 1e13 here) instead of the NaN / noise of a failed fp64 fit
+            assert abs(k.predict(X[5]) - y[5]) < 1e-2 * max(1, abs(y[5]))
+
+
+def test_value_parity_against_exact_likelihood(gold, K):
+    """Pins the conditioning-dependent tolerance band with the binary128 oracle: over the default
+    n = 64 grid the GPU is within 1e-9 of the EXACT likelihood for cond <= 5e6 and within 1e-9 * cond / 5e6 beyond --
+    and is never further from it than 4x the reference's own error + 1e-9."""
+    from oracle import quad
+    g = gold('c2_halton64_default_grid')
+    X, cond = g['X'], g['cond']
+    e, q = g['grid_e'], g['grid_p']
+    th = np.array([[10. ** v for v in row] for row in e])
+    for name in ('f3d', 'fb'):
+        y = g['y_' + name]
+        _, _, nll = K(X, y).grid_search(8, 5, return_nll=True)
+        exact, _ = quad.nll_exact(X, y, th, q)
+        m = np.isfinite(nll) & np.isfinite(exact)
+        err = np.abs(nll[m] - exact[m]) / np.maximum(1, np.abs(exact[m]))
+        band = err <= tol(cond[m])
+        ref_err = np.abs(g['nll_' + name][m] - exact[m]) / np.maximum(1, np.abs(exact[m]))
+        print(f'[{name}] cond<=1e8: max err {err[cond[m] <= 1e8].max():.2e} (reference {ref_err[cond[m] <= 1e8].max():.2e}); '
+              f'cond<=5e6: {err[cond[m] <= 5e6].max():.2e}; outside band: {int((~band).sum())} of {int(m.sum())}')
+        assert err[cond[m] <= 5e6].max() < 1e-9
+        well = cond[m] <= 1e12
+        assert np.all(band[well])
+        # the band is inherent to fp64: over cond <= 1e8 the reference itself is further from the exact value than the GPU
+        w8 = (cond[m] <= 1e8) & np.isfinite(ref_err)
+        assert err[w8].max() <= 2 * ref_err[w8].max() + 1e-9
 
 
 # ------------------------------------------------------------------------------------------ mid / large n
@@ -391,7 +493,7 @@ def test_host_buffer_entry_points_match_device_path(gold, K):
     n0 = _cabi.launch_count()
     _cabi.check(L.sm_krig_nll_grid_host(X.ctypes.data, y.ctypes.data, 36, 2, th_lin.ctypes.data, 8, p_axis.ctypes.data, 5,
                                         0, 1600, nll.ctypes.data, bv.ctypes.data, bi.ctypes.data))
-    assert _cabi.launch_count() - n0 == 5                                      # 2 x tables, likelihood, 2 x argmin
+    assert _cabi.launch_count() - n0 == 7                                      # 2 x tables, likelihood, 2 x double-double pass, 2 x argmin
     assert np.array_equal(nll, nll_d.cpu().numpy(), equal_nan=True) and bi[0] == bi_d == 960
     # sub-range with a global offset
     sub = np.empty(100)
@@ -820,3 +922,65 @@ def test_validation_protocol_against_reference(gold, K, R_):
         def __init__(self, x, fx):
             pass
     assert v.calc_press(X, y, r.predict, NoTrain) == 0.
+
+
+# ------------------------------------------------------------------------------------------ a6' and the other optimisers
+def test_linear_theta_objectives_and_theta_only_optimiser(gold, K, capsys):
+    """_calc_likelihood_opti, _calc_likelihood_opti_theta_only and optimize_theta_only (reference kriging.py:118-128,
+    143-152) against the oracle's restatement of the same calls."""
+    from scipy.optimize import minimize
+    g = gold('c5_kriging_r3')
+    X, y = g['X'], g['y']
+    k = K(X, y)
+    k.records = []
+    v = k._calc_likelihood_opti(np.array([0.05, 0.07, 1.9, 1.4]))
+    assert rel(v, orc.nll_lu(X, y, [0.05, 0.07], [1.9, 1.4])) < 1e-9
+    assert len(k.records) == 1 and list(k.records[0]) == [0.05, 0.07, 1.9, 1.4]
+    assert list(k.get_theta()) == [0.05, 0.07] and list(k.get_p()) == [1.9, 1.4]
+    v2 = k._calc_likelihood_opti_theta_only(np.array([0.02, 0.3]), np.array([1.7, 1.2]))
+    assert rel(v2, orc.nll_lu(X, y, [0.02, 0.3], [1.7, 1.2])) < 1e-9
+    # optimize_theta_only: SLSQP over linear theta at fixed p, bounds 1e-4 .. 1e3, start at 1 (kriging.py:143-152)
+    k2 = K(X, y)
+    k2.update_param([1., 1.], [1.6, 1.6])
+    k2.optimize_theta_only()
+    capsys.readouterr()
+    ref = minimize(lambda t: orc.nll_lu(X, y, t, [1.6, 1.6]), np.ones(2), method='SLSQP', tol=1e-6,
+                   options={'disp': False, 'maxiter': 99999}, bounds=[(0.0001, 1000.)] * 2)
+    assert np.all(np.abs(k2._theta - ref.x) < 1e-4 * np.maximum(1, np.abs(ref.x)))
+    assert list(k2.get_p()) == [1.6, 1.6]
+
+
+def test_basin_restarts_and_multi_start(gold, K, capsys):
+    """'basin' (seeded through numpy's global generator, like the reference's unseeded draws), the deterministic
+    'restarts' search and multi-start SLSQP all end at (or below) the likelihood the plain grid search reaches."""
+    from mylibs.likeli_optimizer import LikeliOptimizer
+    g = gold('c1_kriging_r2')
+    X, y = g['X'], g['y']
+    kg = K(X, y)
+    kg.optimize()
+    ref_nll = kg.calc_likelihood()
+    kb = K(X, y)
+    np.random.seed(3)
+    kb.optimize(opti_algo='basin', record_data=True)
+    out = capsys.readouterr().out
+    assert 'optiTimer:' in out and len(kb.records) > 100
+    assert kb.calc_likelihood() <= ref_nll + 1e-4
+    assert 1e-5 <= kb._theta[0] <= 1e5 and 1. <= kb._p[0] <= 2.
+    runs = []
+    for _ in range(2):
+        kr = K(X, y)
+        kr.optimize(opti_algo='restarts')
+        runs.append((kr._theta.copy(), kr._p.copy(), kr.calc_likelihood()))
+    assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])   # deterministic
+    assert runs[0][2] <= ref_nll + 1e-6
+    # multi-start: the first start IS the reference's single start, so the result can only improve
+    g3 = gold('c5_kriging_r3')
+    k1, k4 = K(g3['X'], g3['y']), K(g3['X'], g3['y'])
+    k1.records = k4.records = None
+    lo1, lo4 = LikeliOptimizer(), LikeliOptimizer()
+    lo4.multi_start = 4
+    r1 = lo1.find(k1._calc_likelihood_opti_exp, 2)
+    r4 = lo4.find(k4._calc_likelihood_opti_exp, 2)
+    assert r4.fun <= r1.fun
+    tops = k4.grid_top(8, 5, 4)
+    assert tops[0] == k4.grid_search(8, 5)[0] and len(tops) == 4

@@ -191,3 +191,27 @@ def test_exp2_core_emulation(tmp_path):
     src = open(os.path.join(root, 'tools', 'exp2_check.c')).read()
     for c in ('1.3538030870311431e-03', '9.163913992275266e-07', '4.135378350676714e-10', '1.399621994296973e-13'):
         assert c in hdr and c in src
+
+
+def test_odometer_and_timer_semantics():
+    """increase_i: little-endian, in place, wraps to zeros (reference likeli_optimizer.py:89-97); TimeTrack interface
+    (reference myutils/time_track.py:18-38)."""
+    import time
+    from mylibs.likeli_optimizer import LikeliOptimizer
+    from myutils.time_track import TimeTrack
+    lo = LikeliOptimizer()
+    d = np.zeros(3)
+    seen = []
+    for _ in range(27):
+        seen.append(tuple(int(v) for v in d))
+        r = lo.increase_i(d, 3)
+        assert r is d
+    assert len(set(seen)) == 27 and seen[1] == (1, 0, 0) and seen[3] == (0, 1, 0) and seen[9] == (0, 0, 1)
+    assert tuple(d) == (0, 0, 0)
+    assert (lo.pBounds, lo.thetaBoundsExp, lo.maxIter, lo.multi_start) == ((1., 2.), (-5, 3), 5e3, 1)
+    t = TimeTrack('unit')
+    time.sleep(0.01)
+    assert t.get_time() >= 0.01
+    t.tic()
+    lap = t.toc()
+    assert 0 <= lap < 0.01 and t.get_time() >= lap

@@ -136,3 +136,87 @@ def test_mid_n256(gold, kk):
     for c in range(0, 24, 5):
         if g['cond'][c] <= 1e8:
             assert rel(orc.nll_chol(X, y, 10. ** g['e'][c], g['p'][c]), g['nll'][c]) < tol(g['cond'][c])
+
+
+# ---------------------------------------------------------------------------------------------- extended precision
+def test_quad_oracle_against_mpmath(gold):
+    """oracle/quad_oracle.c (binary128) == 100-digit mpmath Cholesky, well- and ill-conditioned (kriging_r3 data)."""
+    from oracle import quad, mp_oracle
+    g = gold('c5_kriging_r3')
+    X, y = g['X'], g['y']
+    for th, p in (([0.05, 0.05], [1.9, 1.9]), ([1e-3, 1e-3], [1.8, 1.8]), ([1e-4, 3e-4], [2.0, 1.95])):
+        q, _ = quad.nll_exact(X, y, [th], [p])
+        t = mp_oracle.nll_chol(X, y, th, p)
+        assert abs(q[0] - t) <= 1e-12 * max(1, abs(t)), (th, q[0], t)
+    # SURVEY.md App. E: candidate 998813 of the full C2 grid, exact value -264.6644
+    ic = gold('c2_illcond_f3d')
+    i = int(np.flatnonzero(ic['idx'] == 998813)[0])
+    assert abs(ic['exact'][i] - (-264.6644)) < 1e-3 and abs(ic['ref'][i] - (-268.1161655258276)) < 1e-9
+
+
+def test_c2_illcond_fixture(gold):
+    """The ill-conditioned corner of the C2 grids (oracle/gen_golden.py --only illcond): LAPACK's Cholesky accepts
+    only matrices that ARE positive definite (binary128), the argmin over 'fp64 matrix is PD' is the reference's own
+    998813 on f_3d and 960447 on fb, and every reference value that undercuts it on a non-PD matrix is an artefact."""
+    from oracle import quad
+    from sm_b200 import workloads
+    for resp, want in (('f3d', 998813), ('fb', 960447)):
+        ic, g = gold(f'c2_illcond_{resp}'), gold(f'c2_full_{resp}')
+        assert not (np.isfinite(ic['chol']) & ~np.isfinite(ic['rounded'])).any()
+        pd = np.isfinite(ic['rounded'])
+        best = ic['rounded'][pd].min()
+        if resp == 'f3d':
+            assert int(ic['idx'][pd][np.argmin(ic['rounded'][pd])]) == want == int(g['argmin'])
+        else:
+            assert best > -41.300450780839526                        # nothing in the corner beats the genuine optimum
+            best = -41.300450780839526
+        under = np.isfinite(ic['ref']) & (ic['ref'] < best) & ~pd
+        assert under.sum() >= 1 and np.all(ic['truth'][under] > best)
+        # the fixture is reproducible from the committed oracle
+        X, y = workloads.c2_halton64(resp)
+        e, q = orc.grid_candidates(2, 40, 25)
+        sel = np.arange(0, len(ic['idx']), 97)
+        th = np.array([[10. ** v for v in row] for row in e[ic['idx'][sel]]])
+        r, _ = quad.nll_rounded(X, y, th, q[ic['idx'][sel]])
+        assert np.array_equal(r, ic['rounded'][sel])
+
+
+def test_product_double_double_header_on_host(gold, tmp_path):
+    """csrc/dd.cuh (the arithmetic of the GPU's extended-precision pass) compiled for the host: exp / pow correctly
+    rounded (checked against mpmath), and the double-double likelihood accepts exactly the candidates whose fp64 matrix
+    is positive definite in binary128, with the same value."""
+    import ctypes
+    import os
+    import subprocess
+    import mpmath as mp
+    from sm_b200 import workloads
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = str(tmp_path / 'libdd_check.so')
+    subprocess.run(['g++', '-O2', '-ffp-contract=off', '-fopenmp', '-shared', '-fPIC',
+                    os.path.join(root, 'tools', 'dd_check.cpp'), '-o', so], check=True)
+    lib = ctypes.CDLL(so)
+    dp = ctypes.POINTER(ctypes.c_double)
+    P = lambda a: a.ctypes.data_as(dp)  # noqa: E731
+    rng = np.random.default_rng(0)
+    x = -rng.uniform(0, 40, 3000) * rng.uniform(0, 1, 3000) ** 2
+    out = np.empty_like(x)
+    lib.exp_cr_vec(P(x), len(x), P(out))
+    mp.mp.prec = 200
+    assert all(o == float(mp.exp(mp.mpf(float(v)))) for o, v in zip(out, x))
+    xs, ps = rng.uniform(0, 10, 3000), rng.uniform(1, 2, 3000)
+    lib.pow_cr_vec(P(xs), P(ps), len(xs), P(out))
+    assert all(o == float(mp.power(mp.mpf(float(a)), mp.mpf(float(b)))) for o, a, b in zip(out, xs, ps))
+    ic = gold('c2_illcond_f3d')
+    X, y = workloads.c2_halton64('f3d')
+    e, q = orc.grid_candidates(2, 40, 25)
+    sel = np.flatnonzero(ic['f64_min_pivot'] <= 1e-9)
+    th = np.ascontiguousarray([[10. ** v for v in row] for row in e[ic['idx'][sel]]])
+    qq = np.ascontiguousarray(q[ic['idx'][sel]])
+    nll, mpv = np.empty(len(sel)), np.empty(len(sel))
+    lib.dd_nll_batch(P(np.ascontiguousarray(X)), P(np.ascontiguousarray(y)), 64, 2, P(th), P(qq), ctypes.c_long(len(sel)),
+                     P(nll), P(mpv))
+    r, rmp = ic['rounded'][sel], ic['rounded_min_pivot'][sel]
+    assert np.array_equal(np.isfinite(nll), np.isfinite(r))
+    m = np.isfinite(r)
+    assert np.all(np.abs(nll[m] - r[m]) <= 1e-9 * np.maximum(1, np.abs(r[m])) + 1e-13 / rmp[m])
+    assert int(ic['idx'][sel][np.argmin(nll)]) == 998813
