@@ -100,10 +100,21 @@ int sm_krig_fit(const double* X, const double* y, int n, int k, const double* th
 int sm_krig_predict(const double* X, int n, int k, const double* theta, const double* p, const double* w,
                     double mu, double sigma2, const double* Mop, const double* b, const double* rres,
                     const double* Xq, int64_t Nq, double* y_out, double* mse_out, void* stream);
-/* fit at (theta, p) then predict Nq host-resident queries; scalars[4] as in sm_krig_fit */
+/* fit at (theta, p) then predict Nq host-resident queries; scalars[4] as in sm_krig_fit.  The queries are processed in
+ * chunks over three streams (copy-in, kernel and copy-out of neighbouring chunks overlap when the host buffers are pinned). */
 int sm_krig_fit_predict_host(const double* X, const double* y, int n, int k, const double* theta,
                              const double* p, const double* Xq, int64_t Nq, double* y_out, double* mse_out,
                              double* scalars);
+/* Query mesh on the device: points [begin, begin + count) of the full-factorial mesh with m[d] points per dimension over
+ * [lo[d], hi[d]], last dimension fastest, axis values bit-identical to numpy.linspace(lo, hi, m) -- the plotting meshes of
+ * the reference's examples (examples/kriging_r3.py:27-28, myutils/plot_helper.py:108-113) and BASELINE config 5.
+ * lo, hi, m are HOST arrays of k entries; out (device) receives count * k doubles. */
+int sm_mesh_points(const double* lo, const double* hi, const int64_t* m, int k, int64_t begin, int64_t count, double* out,
+                   void* stream);
+/* sm_krig_fit_predict_host with the queries generated on the device by sm_mesh_points: only the results cross PCIe */
+int sm_krig_fit_predict_mesh_host(const double* X, const double* y, int n, int k, const double* theta, const double* p,
+                                  const double* lo, const double* hi, const int64_t* m, int64_t begin, int64_t count,
+                                  double* y_out, double* mse_out, double* scalars);
 
 /* ---- RBF --------------------------------------------------------------------------------------------------
  * sm_rbf_fit replaces RBF._calc_coefficiants (mylibs/rbf.py:67-80): coeff = Phi^-1 y.  *info (device int):

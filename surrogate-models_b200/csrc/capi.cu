@@ -283,14 +283,36 @@ int sm_krig_nll_batch_host(const double* X, const double* y, int n, int k, const
     return 0;
 }
 
-int sm_krig_fit_predict_host(const double* X, const double* y, int n, int k, const double* theta,
-                             const double* p, const double* Xq, int64_t Nq, double* y_out, double* mse_out,
-                             double* scalars) {
-    if (!X || !y || !theta || !p || !Xq || !y_out || bad_nk(n, k) || Nq < 0) return SM_E_BADARG;
+int sm_mesh_points(const double* lo, const double* hi, const int64_t* m, int k, int64_t begin, int64_t count, double* out,
+                   void* stream) {
+    if (!lo || !hi || !m || !out || k < 1 || k > SM_KMAX || begin < 0 || count < 0) return SM_E_BADARG;
+    long long mm[SM_KMAX];
+    for (int d = 0; d < k; ++d) {
+        if (m[d] < 1) return SM_E_BADARG;
+        mm[d] = m[d];
+    }
+    Launches L;
+    SM_TRY(launch_mesh_points(lo, hi, mm, k, begin, count, out, (cudaStream_t)stream, &L.n));
+    return 0;
+}
+
+namespace {
+// Fit once, then predict the queries in chunks over three streams, each with its own device staging buffers: the
+// host->device copy of chunk c+1 and the device->host copy of chunk c-1 overlap the kernel of chunk c (the caller's
+// buffers should be pinned for the copies to be asynchronous).  mesh != null: the chunk's query points are generated on
+// the device instead of being copied.
+struct MeshArgs {
+    const double *lo, *hi;
+    const int64_t* m;
+    int64_t begin;
+};
+int fit_predict_chunked(const double* X, const double* y, int n, int k, const double* theta, const double* p,
+                        const double* Xq, const MeshArgs* mesh, int64_t Nq, double* y_out, double* mse_out,
+                        double* scalars) {
     HostCall hc;
     SM_TRY(hc.init());
     const int npad = sm_krig_npad(n);
-    double *dX, *dy, *dth, *dp, *dsc, *dw, *db, *dr, *dM, *dXq, *dyo, *dmo = nullptr;
+    double *dX, *dy, *dth, *dp, *dsc, *dw, *db, *dr, *dM = nullptr;
     SM_TRY(hc.up(X, (size_t)n * k, &dX));
     SM_TRY(hc.up(y, (size_t)n, &dy));
     SM_TRY(hc.up(theta, (size_t)k, &dth));
@@ -299,23 +321,75 @@ int sm_krig_fit_predict_host(const double* X, const double* y, int n, int k, con
     SM_TRY(hc.up((const double*)nullptr, (size_t)n, &dw));
     SM_TRY(hc.up((const double*)nullptr, (size_t)npad, &db));
     SM_TRY(hc.up((const double*)nullptr, (size_t)npad, &dr));
-    SM_TRY(hc.up((const double*)nullptr, sm_krig_mop_doubles(n), &dM));
-    SM_TRY(hc.up(Xq, (size_t)Nq * k, &dXq));
-    SM_TRY(hc.up((const double*)nullptr, (size_t)Nq, &dyo));
-    if (mse_out) SM_TRY(hc.up((const double*)nullptr, (size_t)Nq, &dmo));
+    if (mse_out) SM_TRY(hc.up((const double*)nullptr, sm_krig_mop_doubles(n), &dM));
     int rc = sm_krig_fit(dX, dy, n, k, dth, dp, dsc, dw, db, dr, dM, nullptr, hc.st);
     if (rc) return rc;
     double sc[4];
     SM_TRY(hc.down(sc, dsc, 4));
     SM_TRY(cudaStreamSynchronize(hc.st));
     if (scalars) for (int i = 0; i < 4; ++i) scalars[i] = sc[i];
-    if (sc[3] != 0.0) return 0;  // not SPD: in-band (info), nothing to predict with
-    rc = sm_krig_predict(dX, n, k, dth, dp, dw, sc[1], sc[2], dM, db, dr, dXq, Nq, dyo, dmo, hc.st);
-    if (rc) return rc;
-    SM_TRY(hc.down(y_out, dyo, (size_t)Nq));
-    if (mse_out) SM_TRY(hc.down(mse_out, dmo, (size_t)Nq));
-    SM_TRY(cudaStreamSynchronize(hc.st));
-    return 0;
+    if (sc[3] == 1.0 || (mse_out && sc[3] == 3.0)) return 0;  // not positive definite (in-band): nothing to predict with
+    constexpr int NS = 3;
+    int64_t chunk = ((int64_t)48 << 20) / (8 * (int64_t)k);  // 48 MB of query coordinates per chunk
+    if (chunk > Nq) chunk = Nq;
+    if (chunk < 1) chunk = 1;
+    cudaStream_t ss[NS] = {nullptr, nullptr, nullptr};
+    double *bq[NS] = {}, *by[NS] = {}, *bm[NS] = {};
+    int err = 0;
+    Launches L;
+    for (int s = 0; s < NS && !err; ++s) {
+        if (cudaStreamCreateWithFlags(&ss[s], cudaStreamNonBlocking) != cudaSuccess) err = (int)cudaGetLastError();
+        if (!err && cudaMallocAsync((void**)&bq[s], (size_t)chunk * k * 8, ss[s]) != cudaSuccess) err = (int)cudaGetLastError();
+        if (!err && cudaMallocAsync((void**)&by[s], (size_t)chunk * 8, ss[s]) != cudaSuccess) err = (int)cudaGetLastError();
+        if (!err && mse_out && cudaMallocAsync((void**)&bm[s], (size_t)chunk * 8, ss[s]) != cudaSuccess) err = (int)cudaGetLastError();
+    }
+    int64_t done = 0;
+    for (int c = 0; done < Nq && !err; ++c, done += chunk) {
+        const int s = c % NS;
+        const int64_t cnt = (Nq - done < chunk) ? Nq - done : chunk;
+        cudaError_t e = cudaSuccess;
+        if (mesh) {
+            long long mm[SM_KMAX];
+            for (int d = 0; d < k; ++d) mm[d] = mesh->m[d];
+            e = launch_mesh_points(mesh->lo, mesh->hi, mm, k, mesh->begin + done, cnt, bq[s], ss[s], &L.n);
+        } else {
+            e = cudaMemcpyAsync(bq[s], Xq + (size_t)done * k, (size_t)cnt * k * 8, cudaMemcpyHostToDevice, ss[s]);
+        }
+        if (e != cudaSuccess) { err = (int)e; break; }
+        err = sm_krig_predict(dX, n, k, dth, dp, dw, sc[1], sc[2], dM, db, dr, bq[s], cnt, by[s], mse_out ? bm[s] : nullptr, ss[s]);
+        if (err) break;
+        e = cudaMemcpyAsync(y_out + done, by[s], (size_t)cnt * 8, cudaMemcpyDeviceToHost, ss[s]);
+        if (e == cudaSuccess && mse_out) e = cudaMemcpyAsync(mse_out + done, bm[s], (size_t)cnt * 8, cudaMemcpyDeviceToHost, ss[s]);
+        if (e != cudaSuccess) err = (int)e;
+    }
+    for (int s = 0; s < NS; ++s) {
+        if (!ss[s]) continue;
+        if (bq[s]) cudaFreeAsync(bq[s], ss[s]);
+        if (by[s]) cudaFreeAsync(by[s], ss[s]);
+        if (bm[s]) cudaFreeAsync(bm[s], ss[s]);
+        cudaError_t e = cudaStreamSynchronize(ss[s]);
+        if (!err && e != cudaSuccess) err = (int)e;
+        cudaStreamDestroy(ss[s]);
+    }
+    return err;
+}
+}  // namespace
+
+int sm_krig_fit_predict_host(const double* X, const double* y, int n, int k, const double* theta,
+                             const double* p, const double* Xq, int64_t Nq, double* y_out, double* mse_out,
+                             double* scalars) {
+    if (!X || !y || !theta || !p || !Xq || !y_out || bad_nk(n, k) || Nq < 0) return SM_E_BADARG;
+    return fit_predict_chunked(X, y, n, k, theta, p, Xq, nullptr, Nq, y_out, mse_out, scalars);
+}
+
+int sm_krig_fit_predict_mesh_host(const double* X, const double* y, int n, int k, const double* theta, const double* p,
+                                  const double* lo, const double* hi, const int64_t* m, int64_t begin, int64_t count,
+                                  double* y_out, double* mse_out, double* scalars) {
+    if (!X || !y || !theta || !p || !lo || !hi || !m || !y_out || bad_nk(n, k) || begin < 0 || count < 0) return SM_E_BADARG;
+    for (int d = 0; d < k; ++d)
+        if (m[d] < 1) return SM_E_BADARG;
+    const MeshArgs ma{lo, hi, m, begin};
+    return fit_predict_chunked(X, y, n, k, theta, p, nullptr, &ma, count, y_out, mse_out, scalars);
 }
 
 int sm_rbf_fit_host(const double* X, const double* y, int n, int k, int kind, double a, double* coeff, int* info) {

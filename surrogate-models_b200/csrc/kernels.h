@@ -105,6 +105,9 @@ struct PredictArgs {
     double* mse_out;  // [Nq] or null
 };
 cudaError_t launch_krig_predict(const PredictArgs& a, cudaStream_t st, long long* launches);
+// host arrays lo[k], hi[k], m[k]; writes count x k doubles (points begin .. begin + count - 1 of the mesh, last dimension fastest)
+cudaError_t launch_mesh_points(const double* lo, const double* hi, const long long* m, int k, long long begin, long long count,
+                               double* out, cudaStream_t st, long long* launches);
 
 // ---- RBF (rbf.cu)
 cudaError_t launch_rbf_fit(const double* X, const double* y, int n, int k, int kind, double a, double* coeff,

@@ -8,6 +8,8 @@
 // DMMA with M tiles as the A operand and Psi produced *directly in B-fragment order*: lane l computes
 // psi for (sample 8K + l%4 + 4h, query l/4), which is exactly the element mma.m8n8k4 wants from it.
 // With c in hand the mean comes for free as mu + rres . c  (rres = L^-1 (y - 1 mu)).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "fastmath.cuh"
 #include "kernels.h"
@@ -32,31 +34,49 @@ __device__ __forceinline__ double psi_one(const double* __restrict__ xs, const d
 }
 
 // ------------------------------------------------------------------------------------ mean only
+// Thread per query; the samples and weights are staged through shared memory in chunks of `chunk` samples (one chunk
+// when the model fits, which is then loaded once), so n * k is not limited by the shared-memory size.
 template <int KD>
-__global__ void __launch_bounds__(256) krig_predict_mean_kernel(const PredictArgs a) {
+__global__ void __launch_bounds__(256) krig_predict_mean_kernel(const PredictArgs a, const int chunk) {
     extern __shared__ __align__(16) double smem[];
-    double* X_s = smem;                      // [n][k]
-    double* w_s = X_s + (size_t)a.n * a.k;   // [n]
-    double* th_s = w_s + a.n;                // [KMAX]
-    double* p_s = th_s + KMAX;               // [KMAX]
+    double* X_s = smem;                        // [chunk][k]
+    double* w_s = X_s + (size_t)chunk * a.k;   // [chunk]
+    double* th_s = w_s + chunk;                // [KMAX]
+    double* p_s = th_s + KMAX;                 // [KMAX]
     __shared__ PowTables PT;
     PT.init(threadIdx.x, blockDim.x);
-    for (int t = threadIdx.x; t < a.n * a.k; t += blockDim.x) X_s[t] = a.X[t];
-    for (int t = threadIdx.x; t < a.n; t += blockDim.x) w_s[t] = a.w[t];
     if (threadIdx.x < a.k) {
         th_s[threadIdx.x] = a.theta[threadIdx.x];
         p_s[threadIdx.x] = a.p[threadIdx.x];
     }
+    const int k = a.k, n = a.n;
+    const int kk = KD > 0 ? KD : k;
+    const bool single = n <= chunk;
+    if (single) {
+        for (int t = threadIdx.x; t < n * k; t += blockDim.x) X_s[t] = a.X[t];
+        for (int t = threadIdx.x; t < n; t += blockDim.x) w_s[t] = a.w[t];
+    }
     __syncthreads();
-    const int k = a.k;
-    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < a.Nq; q += (long long)gridDim.x * blockDim.x) {
+    const long long Q = (long long)gridDim.x * blockDim.x;
+    const long long nrounds = (a.Nq + Q - 1) / Q;
+    for (long long rd = 0; rd < nrounds; ++rd) {
+        const long long q = rd * Q + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+        const bool live = q < a.Nq;
         double xq[KD > 0 ? KD : KMAX];
-        const int kk = KD > 0 ? KD : k;
 #pragma unroll
-        for (int d = 0; d < kk; ++d) xq[d] = a.Xq[q * k + d];
+        for (int d = 0; d < kk; ++d) xq[d] = live ? a.Xq[q * k + d] : 0.0;
         double acc = 0.0;
-        for (int i = 0; i < a.n; ++i) acc = fma(psi_one<KD>(X_s + (size_t)i * k, xq, th_s, p_s, k, PT), w_s[i], acc);
-        a.y_out[q] = a.mu + acc;
+        for (int i0 = 0; i0 < n; i0 += chunk) {
+            const int m = min(chunk, n - i0);
+            if (!single) {
+                __syncthreads();
+                for (int t = threadIdx.x; t < m * k; t += blockDim.x) X_s[t] = a.X[(size_t)i0 * k + t];
+                for (int t = threadIdx.x; t < m; t += blockDim.x) w_s[t] = a.w[i0 + t];
+                __syncthreads();
+            }
+            for (int i = 0; i < m; ++i) acc = fma(psi_one<KD>(X_s + (size_t)i * k, xq, th_s, p_s, k, PT), w_s[i], acc);
+        }
+        if (live) a.y_out[q] = a.mu + acc;
     }
 }
 
@@ -181,6 +201,139 @@ __global__ void __launch_bounds__(256) krig_predict_mse_kernel(const PredictArgs
     }
 }
 
+// ------------------------------------------------------------------------------------ mean + MSE, n > 128: M streamed from L2
+// One CTA (8 warps) per block of QB = 8 G queries.  Phase 1: the 256 threads compute Psi[npad x QB] once into shared memory,
+// already in B-fragment order (per (K tile, query group) 64 doubles, lane l's pair at [2l, 2l+1]).  Phase 2: the warps take
+// the row tiles of M = L^-1 (snake order, so the triangular row lengths balance) and stream the tiles (Rt, K), K <= Rt, from
+// global memory / L2 -- 512 contiguous bytes per tile, one LDG.128 per lane, each tile feeding 2 G DMMAs -- into
+// C[8 x QB] accumulators; c.c, b.c and rres.c are accumulated per query as the rows complete and combined across warps
+// through shared memory.  Per query the kernel moves n^2/2 * 8 / QB bytes from L2 (n = 1024, QB = 16: 262 KB).
+template <int G>
+__global__ void __launch_bounds__(256) krig_predict_mse_stream_kernel(const PredictArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    constexpr int QB = 8 * G;
+    const int NT = a.npad / 8, k = a.k, n = a.n;
+    double* psi_s = smem;                              // [NT][G][64]
+    double* xq_s = psi_s + (size_t)NT * G * 64;        // [QB][k]
+    double* red_s = xq_s + QB * KMAX;                  // [8 warps][3][QB]
+    double* th_s = red_s + 8 * 3 * QB;                 // [KMAX]
+    double* p_s = th_s + KMAX;                         // [KMAX]
+    __shared__ PowTables PT;
+    __shared__ double bb_s;
+    PT.init(threadIdx.x, blockDim.x);
+    if (threadIdx.x < k) {
+        th_s[threadIdx.x] = a.theta[threadIdx.x];
+        p_s[threadIdx.x] = a.p[threadIdx.x];
+    }
+    if (threadIdx.x < 32) {
+        double s = 0.0;
+        for (int j = threadIdx.x; j < n; j += 32) s = fma(a.b[j], a.b[j], s);
+        s = warp_sum(s);
+        if (threadIdx.x == 0) bb_s = s;
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int qrow = lane >> 2, kq = lane & 3;
+    const long long nblk = (a.Nq + QB - 1) / QB;
+    for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const long long q0 = blk * QB;
+        __syncthreads();  // previous block's psi / reductions consumed
+        for (int t = threadIdx.x; t < QB * k; t += blockDim.x) {
+            long long q = q0 + t / k;
+            if (q >= a.Nq) q = a.Nq - 1;  // clamp: computed, never written
+            xq_s[(t / k) * KMAX + (t % k)] = a.Xq[q * k + (t % k)];
+        }
+        __syncthreads();
+        // ---- phase 1: psi(sample i, query qq) -> fragment slot: tile K = i / 8, group g = qq / 8, lane (qq % 8) * 4 + i % 4, half (i % 8) / 4
+        for (int t = threadIdx.x; t < a.npad * QB; t += blockDim.x) {
+            const int i = t / QB, qq = t % QB;
+            double v = 0.0;
+            if (i < n) v = psi_one<0>(a.X + (size_t)i * k, xq_s + qq * KMAX, th_s, p_s, k, PT);
+            psi_s[((size_t)(i >> 3) * G + (qq >> 3)) * 64 + 2 * ((qq & 7) * 4 + (i & 3)) + ((i & 7) >> 2)] = v;
+        }
+        __syncthreads();
+        // ---- phase 2
+        double cc[G][2], bc[G][2], rc[G][2];
+#pragma unroll
+        for (int g = 0; g < G; ++g) cc[g][0] = cc[g][1] = bc[g][0] = bc[g][1] = rc[g][0] = rc[g][1] = 0.0;
+        for (int idx = wid; idx < NT; idx += 8) {
+            const int round = idx >> 3;
+            int Rt = (round & 1) ? (round * 8 + 7 - wid) : idx;  // snake: long and short rows alternate per warp
+            if (Rt >= NT) Rt = idx;                               // ragged last round: plain order
+            double acc[G][2];
+#pragma unroll
+            for (int g = 0; g < G; ++g) acc[g][0] = acc[g][1] = 0.0;
+            const double* mrow = a.Mop + (size_t)Rt * (Rt + 1) / 2 * 64 + 2 * lane;
+            double2 A = __ldg(reinterpret_cast<const double2*>(mrow));
+            for (int K = 0; K <= Rt; ++K) {
+                const double2 An = (K < Rt) ? __ldg(reinterpret_cast<const double2*>(mrow + (size_t)(K + 1) * 64)) : A;
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const double2 B = *reinterpret_cast<const double2*>(psi_s + ((size_t)K * G + g) * 64 + 2 * lane);
+                    dmma(acc[g][0], acc[g][1], A.x, B.x);
+                    dmma(acc[g][0], acc[g][1], A.y, B.y);
+                }
+                A = An;
+            }
+            const int row = 8 * Rt + qrow;
+            const double bv = a.b[row], rv = a.rres[row];  // zero padded
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const double c = acc[g][e];
+                    cc[g][e] = fma(c, c, cc[g][e]);
+                    bc[g][e] = fma(bv, c, bc[g][e]);
+                    rc[g][e] = fma(rv, c, rc[g][e]);
+                }
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                double x = cc[g][e], y = bc[g][e], z = rc[g][e];
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    x += __shfl_xor_sync(0xffffffffu, x, o);
+                    y += __shfl_xor_sync(0xffffffffu, y, o);
+                    z += __shfl_xor_sync(0xffffffffu, z, o);
+                }
+                if (qrow == 0) {
+                    const int qq = 8 * g + 2 * kq + e;
+                    red_s[(wid * 3 + 0) * QB + qq] = x;
+                    red_s[(wid * 3 + 1) * QB + qq] = y;
+                    red_s[(wid * 3 + 2) * QB + qq] = z;
+                }
+            }
+        __syncthreads();
+        if (threadIdx.x < QB && q0 + threadIdx.x < a.Nq) {
+            double x = 0.0, y = 0.0, z = 0.0;
+            for (int w = 0; w < 8; ++w) {  // fixed order: deterministic
+                x += red_s[(w * 3 + 0) * QB + threadIdx.x];
+                y += red_s[(w * 3 + 1) * QB + threadIdx.x];
+                z += red_s[(w * 3 + 2) * QB + threadIdx.x];
+            }
+            a.y_out[q0 + threadIdx.x] = a.mu + z;
+            const double u = 1.0 - y;
+            const double m = a.sigma2 * (1.0 - x + u * u / bb_s);
+            a.mse_out[q0 + threadIdx.x] = m > 0.0 ? m : 0.0;
+        }
+    }
+}
+
+template <int G>
+static cudaError_t launch_mse_stream(const PredictArgs& a, cudaStream_t st) {
+    const size_t smem = ((size_t)(a.npad / 8) * G * 64 + 8 * G * KMAX + 8 * 3 * 8 * G + 2 * KMAX) * 8;
+    cudaError_t e = cudaFuncSetAttribute(krig_predict_mse_stream_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long long nblk = (a.Nq + 8 * G - 1) / (8 * G);
+    int per_sm = (int)((size_t)(227 * 1024) / (smem + 12 * 1024));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+    long long grid = (long long)sm_count() * per_sm;
+    if (grid > nblk) grid = nblk;
+    krig_predict_mse_stream_kernel<G><<<(int)grid, 256, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------ generic MSE (any n)
 // thread per query, psi staged in a global scratch [n][Q] (coalesced), M read tile-wise (L1 broadcast)
 __global__ void __launch_bounds__(256) krig_predict_mse_generic_kernel(const PredictArgs a, double* __restrict__ psi_ws) {
@@ -225,13 +378,15 @@ __global__ void __launch_bounds__(256) krig_predict_mse_generic_kernel(const Pre
 // ------------------------------------------------------------------------------------ launchers
 template <int KD>
 static cudaError_t launch_mean(const PredictArgs& a, cudaStream_t st) {
-    const size_t smem = ((size_t)a.n * a.k + a.n + 2 * KMAX) * 8;
+    int chunk = (int)((size_t)(64 * 1024) / ((size_t)(a.k + 1) * 8));  // samples staged per pass: <= 64 KB
+    if (chunk > a.n) chunk = a.n;
+    const size_t smem = ((size_t)chunk * (a.k + 1) + 2 * KMAX) * 8;
     cudaError_t e = cudaFuncSetAttribute(krig_predict_mean_kernel<KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     long long grid = (a.Nq + 255) / 256;
     const long long cap = (long long)sm_count() * 8;
     if (grid > cap) grid = cap;
-    krig_predict_mean_kernel<KD><<<(int)grid, 256, smem, st>>>(a);
+    krig_predict_mean_kernel<KD><<<(int)grid, 256, smem, st>>>(a, chunk);
     return cudaGetLastError();
 }
 
@@ -259,12 +414,53 @@ static cudaError_t launch_mse_k(const PredictArgs& a, cudaStream_t st) {
     }
 }
 
+// ------------------------------------------------------------------------------------ query mesh on the device
+// Points [begin, begin + count) of the full-factorial mesh prod_d m[d] over [lo_d, hi_d], last dimension fastest (the
+// row-major order of np.meshgrid(..., indexing='ij')), axis values bit-identical to np.linspace(lo, hi, m): i * step + lo
+// with step = (hi - lo) / (m - 1) as two roundings, the last point exactly hi.  Replaces the host-side mesh of
+// examples/kriging_r3.py:27-28 so that the 1e8 query points of BASELINE config 5 never cross PCIe.
+struct MeshSpec {
+    double lo[KMAX], hi[KMAX];
+    long long m[KMAX];
+    int k;
+};
+__global__ void __launch_bounds__(256) mesh_points_kernel(const MeshSpec ms, long long begin, long long count, double* __restrict__ out) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < count; t += (long long)gridDim.x * blockDim.x) {
+        long long idx = begin + t;
+        for (int d = ms.k - 1; d >= 0; --d) {
+            const long long i = idx % ms.m[d];
+            idx /= ms.m[d];
+            double v = ms.lo[d];
+            if (ms.m[d] > 1) {
+                const double step = (ms.hi[d] - ms.lo[d]) / (double)(ms.m[d] - 1);
+                v = (i == ms.m[d] - 1) ? ms.hi[d] : __dadd_rn(__dmul_rn((double)i, step), ms.lo[d]);
+            }
+            out[t * ms.k + d] = v;
+        }
+    }
+}
+cudaError_t launch_mesh_points(const double* lo, const double* hi, const long long* m, int k, long long begin, long long count,
+                               double* out, cudaStream_t st, long long* launches) {
+    if (count <= 0) return cudaSuccess;
+    MeshSpec ms{};
+    ms.k = k;
+    for (int d = 0; d < k; ++d) {
+        ms.lo[d] = lo[d];
+        ms.hi[d] = hi[d];
+        ms.m[d] = m[d];
+    }
+    long long grid = (count + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (grid > cap) grid = cap;
+    mesh_points_kernel<<<(int)grid, 256, 0, st>>>(ms, begin, count, out);
+    if (launches) *launches += 1;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_krig_predict(const PredictArgs& a, cudaStream_t st, long long* launches) {
     if (a.Nq <= 0) return cudaSuccess;
     if (launches) *launches += 1;
     if (!a.mse_out) {
-        const size_t smem = ((size_t)a.n * a.k + a.n + 2 * KMAX) * 8;
-        if (smem > smem_optin()) return cudaErrorInvalidValue;  // n*k beyond the staged-sample capacity
         switch (a.k) {
             case 1: return launch_mean<1>(a, st);
             case 2: return launch_mean<2>(a, st);
@@ -278,7 +474,18 @@ cudaError_t launch_krig_predict(const PredictArgs& a, cudaStream_t st, long long
     if (NT <= 4) return launch_mse_k<4, 4>(a, st);
     if (NT <= 8) return launch_mse_k<8, 2>(a, st);
     if (NT <= 16) return launch_mse_k<16, 1>(a, st);
-    // generic path
+    // n > 128: Psi block in shared memory, M streamed from L2 on DMMA; as many queries per block as shared memory takes
+    {
+        static const bool force_generic = [] { const char* v = getenv("SMB_PREDICT_GENERIC"); return v && v[0] == '1'; }();
+        const size_t per_g = (size_t)NT * 64 * 8;  // bytes of Psi per group of 8 queries
+        const size_t room = smem_optin() > 24 * 1024 ? smem_optin() - 24 * 1024 : 0;
+        if (!force_generic) {
+            if (4 * per_g <= room && 4 * per_g <= 96 * 1024) return launch_mse_stream<4>(a, st);
+            if (2 * per_g <= room) return launch_mse_stream<2>(a, st);
+            if (per_g <= room) return launch_mse_stream<1>(a, st);
+        }
+    }
+    // generic path (n beyond ~3000, or SMB_PREDICT_GENERIC=1 for the cross-check in the tests)
     long long grid = (a.Nq + 255) / 256;
     const long long cap = (long long)sm_count() * 4;
     if (grid > cap) grid = cap;

@@ -328,11 +328,13 @@ class Kriging:
         return self.predict_batch(xq)[0]
 
     # ------------------------------------------------------------------ batched entry points (additive)
-    def likelihood_batch(self, log10_theta, p, return_best=False):
+    def likelihood_batch(self, log10_theta, p, return_best=False, distributed=None, gather=True):
         """nll for every row of an explicit candidate list: log10_theta[C,k], p[C,k] -> nll[C].
-        Replaces a loop of _calc_likelihood_opti_exp calls (kriging.py:130-141)."""
-        L = _cabi.lib()
-        d = self._dev()
+        Replaces a loop of _calc_likelihood_opti_exp calls (kriging.py:130-141).
+        With torch.distributed initialised (and distributed is not False) the rows are sharded contiguously over the
+        ranks (every rank holds the replicated samples); the per-rank (nll_min, row) pairs cross the
+        interconnect as one 16-byte all_gather and, with gather=True, the nll slices are all-gathered so every rank
+        returns the full vector (gather=False: this rank's rows [lo, hi) only).  Row indices are global."""
         e = np.atleast_2d(np.asarray(log10_theta, dtype=np.float64))
         q = np.atleast_2d(np.asarray(p, dtype=np.float64))
         if e.shape != q.shape or e.shape[1] != self._k:
@@ -340,15 +342,24 @@ class Kriging:
         C = e.shape[0]
         if C == 0:
             return (np.empty(0), float('inf'), -1) if return_best else np.empty(0)
-        out, bv, bi = self._likelihood_list(np.power(10., e), q)  # 10.**e, vectorised
-        nanrow = np.isnan(e).any(axis=1) | np.isnan(q).any(axis=1)
+        rank, world = dist.rank_world(distributed)
+        lo, hi = dist.shard_range(C, rank, world)
+        nll_d, bv_d, bi_d = self._likelihood_list_dev(np.power(10., e[lo:hi]), q[lo:hi], lo)  # 10.**e, vectorised
+        if world > 1:
+            bv, bi = dist.global_first_min_dev(bv_d, bi_d) if return_best else (None, None)
+            if gather:
+                nll_d, lo, hi = dist.gather_slices(nll_d, C), 0, C
+        elif return_best:
+            bv, bi = float(bv_d.item()), int(bi_d.item())
+        out = nll_d.cpu().numpy()
+        nanrow = np.isnan(e[lo:hi]).any(axis=1) | np.isnan(q[lo:hi]).any(axis=1)
         out[nanrow] = np.nan  # NaN parameters -> NaN (kriging.py:131-132)
         if return_best:
             return out, bv, bi
         return out
 
-    def _likelihood_list(self, theta_lin, p):
-        """sm_krig_nll_batch on linear theta[C,k], p[C,k] -> (nll[C], best value, best index)"""
+    def _likelihood_list_dev(self, theta_lin, p, idx_base=0):
+        """sm_krig_nll_batch on linear theta[C,k], p[C,k]: device tensors (nll[C], best value, best index + idx_base)"""
         L = _cabi.lib()
         d = self._dev()
         C = theta_lin.shape[0]
@@ -357,11 +368,16 @@ class Kriging:
         nll = device.empty(C)
         bv, bi = device.empty(1), device.empty(1, dtype=_int64())
         _cabi.check(L.sm_krig_nll_batch(device.ptr(d['X']), device.ptr(d['y']), self._n, self._k, device.ptr(theta),
-                                        device.ptr(pd), C, 0, device.ptr(nll), device.ptr(bv), device.ptr(bi),
+                                        device.ptr(pd), C, int(idx_base), device.ptr(nll), device.ptr(bv), device.ptr(bi),
                                         device.stream()))
+        return nll, bv, bi
+
+    def _likelihood_list(self, theta_lin, p):
+        """sm_krig_nll_batch on linear theta[C,k], p[C,k] -> (nll[C], best value, best index), on the host"""
+        nll, bv, bi = self._likelihood_list_dev(theta_lin, p)
         return nll.cpu().numpy(), float(bv.item()), int(bi.item())
 
-    def likelihood_grid(self, theta_sections=8, p_sections=5, c_begin=0, c_count=None, return_nll=True):
+    def likelihood_grid(self, theta_sections=8, p_sections=5, c_begin=0, c_count=None, return_nll=True, as_device=False):
         """nll over candidates [c_begin, c_begin + c_count) of LikeliOptimizer.generate_grid's enumeration
         (likeli_optimizer.py:50-97) on THIS device.  Returns (best_val, best_idx, nll or None);
         best_idx is the global flat index of the first strict minimum, -1 if nothing is finite."""
@@ -378,6 +394,8 @@ class Kriging:
         _cabi.check(L.sm_krig_nll_grid(device.ptr(d['X']), device.ptr(d['y']), self._n, self._k, device.ptr(th_lin), T,
                                        device.ptr(pa), P, int(c_begin), c_count, device.ptr(nll), device.ptr(bv),
                                        device.ptr(bi), device.stream()))
+        if as_device:  # no synchronisation: (1 x float64, 1 x int64, nll) stay on the device
+            return bv, bi, nll
         return float(bv.item()), int(bi.item()), nll
 
     def grid_search(self, theta_sections=8, p_sections=5, distributed=None, return_nll=False):
@@ -388,24 +406,32 @@ class Kriging:
         total = (T ** self._k) * (P ** self._k)
         rank, world = dist.rank_world(distributed)
         lo, hi = dist.shard_range(total, rank, world)
-        bv, bi, nll = self.likelihood_grid(T, P, lo, hi - lo, return_nll=return_nll)
-        if world > 1:
-            bv, bi = dist.global_first_min(bv, bi)
+        bv_d, bi_d, nll = self.likelihood_grid(T, P, lo, hi - lo, return_nll=return_nll, as_device=True)
+        bv, bi = dist.global_first_min_dev(bv_d, bi_d)  # one 16-byte all_gather + one 16-byte read-back
         param = None if bi < 0 else grid_param(self._k, T, P, bi)
         if return_nll:
             return param, bi, nll.cpu().numpy()
         return param, bi
 
-    def predict_batch(self, x_query, return_mse=False):
+    def predict_batch(self, x_query, return_mse=False, distributed=None, gather=True):
         """Mean (and ordinary-Kriging MSE) at many query points: Xq[Nq,k] -> y[Nq] (, mse[Nq]).
-        Replaces a Python loop over Kriging.predict (kriging.py:206-220)."""
+        Replaces a Python loop over Kriging.predict (kriging.py:206-220).
+        With torch.distributed initialised (and distributed is not False) every rank, holding the same fitted model,
+        predicts the contiguous row range [lo, hi) of Xq; gather=True all-gathers the slices so every rank returns all
+        Nq results, gather=False returns this rank's rows only (results stay sharded)."""
         if self._fit is None and not self._fit_stale:  # the reference predicts with whatever update_param left behind
             raise _cabi.SurrogateB200Error('predict before update_param / train: no fitted state')
         self._ensure_fit()
         xq = np.asarray(x_query, dtype=np.float64)
         if xq.ndim == 1:
             xq = xq.reshape(-1, self._k)
-        y, mse = self.predict_device(device.to_dev(xq), return_mse)
+        nq = xq.shape[0]
+        rank, world = dist.rank_world(distributed)
+        lo, hi = dist.shard_range(nq, rank, world)
+        y, mse = self.predict_device(device.to_dev(xq[lo:hi]), return_mse)
+        if world > 1 and gather:
+            y = dist.gather_slices(y, nq)
+            mse = dist.gather_slices(mse, nq) if return_mse else None
         if return_mse:
             return y.cpu().numpy(), mse.cpu().numpy()
         return y.cpu().numpy()

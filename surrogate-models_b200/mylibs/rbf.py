@@ -92,12 +92,21 @@ class RBF:
         xq = np.array([[x_pred[i] for i in range(self._k)]], dtype=np.float64)
         return self.predict_batch(xq)[0].item()
 
-    def predict_batch(self, x_query):
-        """f(x) for many query points: Xq[Nq,k] -> y[Nq] (replaces a loop over predict)"""
+    def predict_batch(self, x_query, distributed=None, gather=True):
+        """f(x) for many query points: Xq[Nq,k] -> y[Nq] (replaces a loop over predict).  With torch.distributed
+        initialised the query rows are sharded contiguously over the ranks (each holds the same coefficients);
+        gather=True returns all Nq values on every rank, gather=False this rank's rows only."""
+        from sm_b200 import dist
         xq = np.asarray(x_query, dtype=np.float64)
         if xq.ndim == 1:
             xq = xq.reshape(-1, self._k)
-        return self.predict_device(device.to_dev(xq)).cpu().numpy()
+        nq = xq.shape[0]
+        rank, world = dist.rank_world(distributed)
+        lo, hi = dist.shard_range(nq, rank, world)
+        y = self.predict_device(device.to_dev(xq[lo:hi]))
+        if world > 1 and gather:
+            y = dist.gather_slices(y, nq)
+        return y.cpu().numpy()
 
     def predict_device(self, xq_dev):
         if self._coeff is None:

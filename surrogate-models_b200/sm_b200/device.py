@@ -32,5 +32,20 @@ def ptr(t):
     return None if t is None else t.data_ptr()
 
 
+def mesh_points(lo, hi, m, begin=0, count=None):
+    """rows [begin, begin + count) of the full-factorial query mesh (last dimension fastest), generated on the device
+    (sm_mesh_points); bit-identical to stacking numpy.linspace axes with meshgrid(indexing='ij')."""
+    lo = np.ascontiguousarray(lo, dtype=np.float64)
+    hi = np.ascontiguousarray(hi, dtype=np.float64)
+    m = np.ascontiguousarray(m, dtype=np.int64)
+    k = lo.shape[0]
+    total = int(np.prod(m))
+    count = total - begin if count is None else int(count)
+    out = empty((count, k))
+    _cabi.check(_cabi.lib().sm_mesh_points(lo.ctypes.data, hi.ctypes.data, m.ctypes.data, k, int(begin), count, ptr(out),
+                                           stream()))
+    return out
+
+
 def stream():
     return torch.cuda.current_stream().cuda_stream

@@ -49,6 +49,27 @@ def global_first_min(val, idx, device=None, group=None):
     return first_min_pairs(vs.tolist(), is_.tolist())
 
 
+def global_first_min_dev(val_t, idx_t, group=None):
+    """Same reduction as global_first_min, fed straight from the kernel's output buffers (val_t: 1 x float64, idx_t:
+    1 x int64, on the device for nccl / on the host for gloo): ONE 16-byte all_gather (the index travels as the bit pattern
+    of a float64), the lexicographic reduction runs on the gathered tensor, and a single 16-byte copy brings the result
+    to the host -- one synchronisation per step instead of the six of the host-scalar version."""
+    pair = torch.stack([val_t.reshape(()), idx_t.reshape(()).view(torch.float64)])
+    if td.is_available() and td.is_initialized() and td.get_world_size(group) > 1:
+        world = td.get_world_size(group)
+        out = torch.empty(2 * world, dtype=torch.float64, device=pair.device)
+        td.all_gather_into_tensor(out, pair, group=group)
+        vals, idxs = out[0::2], out[1::2].contiguous().view(torch.int64)
+        inf = torch.full_like(vals, float('inf'))
+        vals = torch.where((idxs >= 0) & ~torch.isnan(vals), vals, inf)     # NaN and "nothing finite" never win
+        vmin = vals.min()
+        imin = torch.where(vals == vmin, idxs, torch.full_like(idxs, torch.iinfo(torch.int64).max)).min()
+        imin = torch.where(torch.isinf(vmin), torch.full_like(imin, -1), imin)
+        pair = torch.stack([vmin, imin.view(torch.float64)])
+    host = pair.cpu()
+    return float(host[0]), int(host[1:].view(torch.int64)[0])
+
+
 def gather_slices(local, total, group=None):
     """concatenate per-rank contiguous slices (shard_range order) of a 1-D result on every rank"""
     if not (td.is_available() and td.is_initialized()) or td.get_world_size(group) == 1:

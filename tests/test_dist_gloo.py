@@ -33,6 +33,13 @@ def _worker(rank, world, port, q):
         nv, ni = dist.global_first_min(float('inf') if rank == 0 else 2.0, -1 if rank == 0 else 77)
         gathered = dist.gather_slices(torch.from_numpy(nll[lo:hi].copy()), nll.shape[0])
         ok = np.array_equal(gathered.numpy(), nll, equal_nan=True)
+        # the packed 16-byte variant fed from (value, index) tensors: same three answers
+        t = lambda v, i: (torch.tensor([v], dtype=torch.float64), torch.tensor([i], dtype=torch.int64))  # noqa: E731
+        ok = ok and dist.global_first_min_dev(*t(lv, lidx)) == (bv, bi)
+        ok = ok and dist.global_first_min_dev(*t(1.25, 100 - rank)) == (tv, ti)
+        ok = ok and dist.global_first_min_dev(*t(float('inf') if rank == 0 else 2.0, -1 if rank == 0 else 77)) == (nv, ni)
+        ok = ok and dist.global_first_min_dev(*t(float('nan') if rank == 0 else float('inf'), 5 if rank == 0 else -1)) == (float('inf'), -1)
+        ok = ok and dist.global_first_min_dev(*t(-3.5, (1 << 40) + rank)) == (-3.5, 1 << 40)   # indices beyond 2^32 survive
         q.put((rank, bv, bi, tv, ti, nv, ni, ok, dist.rank_world()))
     finally:
         td.destroy_process_group()

@@ -984,3 +984,83 @@ def test_basin_restarts_and_multi_start(gold, K, capsys):
     assert r4.fun <= r1.fun
     tops = k4.grid_top(8, 5, 4)
     assert tops[0] == k4.grid_search(8, 5)[0] and len(tops) == 4
+
+
+# ------------------------------------------------------------------------------------------ prediction, round 2
+def test_device_mesh_bit_identical_to_numpy(K):
+    from sm_b200 import device
+    got = device.mesh_points([-2., -2.], [12., 12.], [317, 211]).cpu().numpy()
+    ax0, ax1 = np.linspace(-2., 12., 317), np.linspace(-2., 12., 211)
+    g0, g1 = np.meshgrid(ax0, ax1, indexing='ij')
+    assert np.array_equal(got, np.stack([g0.ravel(), g1.ravel()], axis=1))
+    sq = device.mesh_points([-2., -2.], [12., 12.], [100, 100], begin=3700, count=1234).cpu().numpy()
+    assert np.array_equal(sq, workloads.c5_query_mesh(100)[3700:3700 + 1234])       # the bench's host-side generator
+    g3 = device.mesh_points([0., 1., -1.], [1., 1., 4.], [3, 1, 5]).cpu().numpy()
+    a, b, c = np.meshgrid(np.linspace(0, 1, 3), np.linspace(1, 1, 1), np.linspace(-1, 4, 5), indexing='ij')
+    assert np.array_equal(g3, np.stack([a.ravel(), b.ravel(), c.ravel()], axis=1))
+
+
+def test_chunked_host_prediction_and_mesh_entry_point(gold, K):
+    """sm_krig_fit_predict_host (chunked over three streams) and sm_krig_fit_predict_mesh_host == the device path"""
+    g = gold('c5_kriging_r3')
+    X, y = np.ascontiguousarray(g['X']), np.ascontiguousarray(g['y'])
+    th, p = np.array([0.05, 0.05]), np.array([1.9, 1.9])
+    k = K(X, y)
+    k.update_param(th, p)
+    m = 2300                                                             # 5.29e6 queries = 84.6 MB of coordinates: 2 chunks
+    xq = workloads.c5_query_mesh(m)
+    yd, md = k.predict_batch(xq, return_mse=True)
+    L = _cabi.lib()
+    yh, mh, sc = np.empty(m * m), np.empty(m * m), np.empty(4)
+    _cabi.check(L.sm_krig_fit_predict_host(X.ctypes.data, y.ctypes.data, 36, 2, th.ctypes.data, p.ctypes.data, xq.ctypes.data,
+                                           m * m, yh.ctypes.data, mh.ctypes.data, sc.ctypes.data))
+    assert np.array_equal(yh, yd) and np.array_equal(mh, md) and sc[3] == 0.0
+    lo, hi, mm = np.array([-2., -2.]), np.array([12., 12.]), np.array([m, m], dtype=np.int64)
+    ym, mmse = np.empty(m * m - 17), np.empty(m * m - 17)
+    _cabi.check(L.sm_krig_fit_predict_mesh_host(X.ctypes.data, y.ctypes.data, 36, 2, th.ctypes.data, p.ctypes.data,
+                                                lo.ctypes.data, hi.ctypes.data, mm.ctypes.data, 17, m * m - 17,
+                                                ym.ctypes.data, mmse.ctypes.data, sc.ctypes.data))
+    assert np.array_equal(ym, yd[17:]) and np.array_equal(mmse, md[17:])
+    ymean = np.empty(1000)
+    _cabi.check(L.sm_krig_fit_predict_host(X.ctypes.data, y.ctypes.data, 36, 2, th.ctypes.data, p.ctypes.data, xq.ctypes.data,
+                                           1000, ymean.ctypes.data, None, None))
+    assert np.max(rel(ymean, yd[:1000])) < 1e-12                          # mean-only kernel vs the MSE kernel's mean
+
+
+@pytest.mark.parametrize('n,k_,nq', [(137, 2, 45), (361, 5, 300), (1024, 8, 131), (2100, 3, 40)])
+def test_streamed_mse_prediction_large_n(K, n, k_, nq):
+    """n > 128: the MSE contraction streams L^-1 from L2 on DMMA (4 / 2 / 1 query groups per CTA depending on n);
+    ragged query counts; against the oracle's Cholesky form."""
+    rng = np.random.default_rng(n)
+    X = rng.uniform(0, 1, (n, k_))
+    y = np.sin(3 * X.sum(axis=1)) + X[:, 0] ** 2
+    th, p = 10. ** rng.uniform(-0.5, 1.0, k_), rng.uniform(1.2, 1.9, k_)
+    k = K(X, y)
+    k.update_param(th, p)
+    xq = rng.uniform(0, 1, (nq, k_))
+    xq[0] = X[3]
+    yy, mse = k.predict_batch(xq, return_mse=True)
+    yr, mr = orc.predict_chol(X, y, th, p, xq, True)
+    s2 = k._fit['sigma2']
+    c = orc.cond2(orc.corr_matrix(X, th, p))
+    scale = max(1.0, c / 1e7)
+    assert np.max(rel(yy, yr)) < 1e-9 * scale and np.max(np.abs(mse - mr)) < 1e-9 * scale * s2, (c, np.max(rel(yy, yr)))
+    assert np.max(rel(k.predict_batch(xq), yr)) < 1e-9 * scale
+    assert mse[0] <= 1e-7 * scale * s2 and np.all(mse >= 0)
+
+
+def test_mean_prediction_beyond_one_shared_memory_stage(K):
+    """n = 4096, k = 8 -- (n k + n) * 8 B = 295 KB does not fit one CTA; the mean kernel stages
+    the samples in chunks.  Against the oracle."""
+    rng = np.random.default_rng(9)
+    n, k_ = 4096, 8
+    X = rng.uniform(0, 1, (n, k_))
+    y = np.sin(3 * X.sum(axis=1)) + X[:, 0] ** 2
+    th, p = np.full(k_, 8.0), np.full(k_, 1.5)
+    k = K(X, y)
+    k.update_param(th, p)
+    xq = rng.uniform(0, 1, (50, k_))
+    got = k.predict_batch(xq)
+    f = orc.fit_chol(X, y, th, p)
+    ref = orc.predict_chol(X, y, th, p, xq, False)
+    assert rel(k._fit['mu'], f['mu']) < 1e-9 and np.max(rel(got, ref)) < 1e-8
