@@ -224,6 +224,33 @@ def predict_lu(X, y, theta, p, Xq):
     return mu + (psi @ Rinv) @ (y - one * mu)
 
 
+def predict_lu_loops(X, y, theta, p, Rinv, mu, x_pred):
+    """Statement-by-statement port of Kriging.predict (kriging.py:206-220) on the state update_param left behind
+    (Rinv = _core_mat_inv, mu = _mu): interpreted psi loop with scalar pow / math.exp, then the O(n^2) product
+    psi^T R^-1 (y - 1 mu) -- per query, as the reference does.  This is what bench.py's prediction cpu_baseline times."""
+    n, k = X.shape
+    one = np.ones((n, 1)).flatten()
+    psi = np.ones((n, 1)).flatten()
+    for i in range(0, n):
+        s = 0.
+        for ik in range(0, k):
+            s += theta[ik] * (abs(X[i][ik] - x_pred[ik]) ** p[ik])
+        psi[i] = math.exp(-s)
+    return mu + np.transpose(psi) @ Rinv @ (y - one * mu)
+
+
+def rbf_predict_loops(X, coeff, a, x_pred):
+    """Statement-by-statement port of RBF.predict with the gaussian kernel (rbf.py:85-103,111-112)."""
+    res = 0.
+    for i in range(0, X.shape[0]):
+        rad_sum = 0.
+        for ik in range(0, X.shape[1]):
+            rad_sum += (x_pred[ik] - X[i][ik]) ** 2.
+        radius = math.sqrt(rad_sum)
+        res += coeff[i] * math.e ** (-((a * radius) ** 2))
+    return res
+
+
 def fit_chol(X, y, theta, p):
     """Fitted state the GPU path keeps: L, M = L^-1, a = L^-1 y, b = L^-1 1, mu, sigma2,
     w = R^-1 (y - 1 mu) = M^T (a - mu b)."""

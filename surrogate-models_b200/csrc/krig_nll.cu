@@ -16,6 +16,7 @@
 //   list mode: LG[d][i][j] = ln|dx| tabulated once, |dx|^p = exp(p * LG)
 #include <cstdlib>
 
+#include "dd.cuh"
 #include "tile_chol.cuh"
 #include "kernels.h"
 
@@ -36,7 +37,7 @@ __global__ void dtab_kernel(const double* __restrict__ X, int n, int k, int npad
         double v = (i == j) ? 0.0 : 1.7976931348623157e308;
         if (i < n && j < n) {
             const double dx = fabs(X[(size_t)i * k + d] - X[(size_t)j * k + d]);
-            v = pow(dx, p_axis[q]);  // abs(dx) ** p  (kriging.py:75); 0 ** p = 0
+            v = pow_cr(dx, p_axis[q]);  // abs(dx) ** p  (kriging.py:75), correctly rounded like glibc's; 0 ** p = 0
         }
         D[t] = v;
     }

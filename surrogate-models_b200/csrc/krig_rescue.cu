@@ -47,17 +47,27 @@ __device__ __forceinline__ dd warp_sum_dd(dd v) {  // result valid on lane 0
 
 // packed lower triangle of the (n + 2) x (n + 2) augmented matrix: rows n, n + 1 hold y^T and 1^T
 __device__ __forceinline__ size_t tri(int i, int j) { return (size_t)i * (i + 1) / 2 + j; }
+// flat index t of a lower triangle (row-major, diagonal included) -> (row r, column c <= r); used to spread the
+// triangular loops evenly over the threads (a row-per-warp split leaves ~85 % of the lanes idle at n = 64)
+__device__ __forceinline__ void tri_rc(int t, int& r, int& c) {
+    r = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+    while (r * (r + 1) / 2 > t) --r;
+    while ((r + 1) * (r + 2) / 2 <= t) ++r;
+    c = t - r * (r + 1) / 2;
+}
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) krig_rescue_kernel(const NllArgs a, const int mode, const long long* __restrict__ list,
                                                               const unsigned long long* __restrict__ cnt, dd* __restrict__ gws,
-                                                              const size_t ws_stride, const FitOut fo) {
+                                                              const size_t ws_stride, const FitOut fo, const bool tab_rowmajor) {
     extern __shared__ __align__(16) unsigned char rsm[];
     double* th = reinterpret_cast<double*>(rsm);  // [KMAX]
     double* pw = th + KMAX;                        // [KMAX]
-    dd* A = ws_stride ? gws + (size_t)blockIdx.x * ws_stride : reinterpret_cast<dd*>(pw + KMAX);
+    size_t* toff = reinterpret_cast<size_t*>(pw + KMAX);  // [KMAX] offset of table (d, q_d) in a.dtab
+    dd* A = ws_stride ? gws + (size_t)blockIdx.x * ws_stride : reinterpret_cast<dd*>(toff + KMAX);
+    const bool tabbed = (mode == 0) && a.dtab != nullptr && tab_rowmajor;
     const int n = a.n, k = a.k, m = n + 2;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = THREADS / 32;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned long long total = *cnt;
     __shared__ dd sh_mu;
     __shared__ int sh_ok;
@@ -77,6 +87,7 @@ __global__ void __launch_bounds__(THREADS) krig_rescue_kernel(const NllArgs a, c
                 }
                 th[d] = a.theta_axis[ti % a.T];
                 pw[d] = a.p_axis[pi % a.P];
+                toff[d] = ((size_t)d * a.P + (size_t)(pi % a.P)) * a.npad * a.npad;
             } else {
                 th[d] = a.theta[c * k + d];
                 pw[d] = a.p[c * k + d];
@@ -89,13 +100,18 @@ __global__ void __launch_bounds__(THREADS) krig_rescue_kernel(const NllArgs a, c
             continue;
         }
         // ---- entries: the reference's own composition, correctly rounded
-        for (int i = wid; i < n; i += nwarps)
-            for (int j = lane; j <= i; j += 32) {
-                double s = 0.0;
+        for (int t = threadIdx.x; t < n * (n + 1) / 2; t += THREADS) {
+            int i, j;
+            tri_rc(t, i, j);
+            double s = 0.0;
+            if (tabbed) {  // grid mode, row-major |dx|^p tables (built with the same correctly rounded pow)
+                for (int d = 0; d < k; ++d) s = __dadd_rn(s, __dmul_rn(th[d], a.dtab[toff[d] + (size_t)i * a.npad + j]));
+            } else {
                 for (int d = 0; d < k; ++d)
                     s = __dadd_rn(s, __dmul_rn(th[d], pow_cr(fabs(a.X[(size_t)i * k + d] - a.X[(size_t)j * k + d]), pw[d])));
-                A[tri(i, j)] = dd{exp_cr(-s), 0.0};
             }
+            A[t] = dd{exp_cr(-s), 0.0};
+        }
         for (int j = threadIdx.x; j < n; j += THREADS) {
             A[tri(n, j)] = dd{a.y[j], 0.0};
             A[tri(n + 1, j)] = dd{1.0, 0.0};
@@ -114,10 +130,12 @@ __global__ void __launch_bounds__(THREADS) krig_rescue_kernel(const NllArgs a, c
             const dd linv = dd_recip(dd_sqrt(d));
             for (int i = j + 1 + threadIdx.x; i < m; i += THREADS) A[tri(i, j)] = dd_mul(A[tri(i, j)], linv);
             __syncthreads();
-            for (int i = j + 1 + wid; i < m; i += nwarps) {
-                const dd lij = A[tri(i, j)];
-                const int cend = (i < n) ? i : n - 1;
-                for (int cc = j + 1 + lane; cc <= cend; cc += 32) A[tri(i, cc)] = dd_fnma(lij, A[tri(cc, j)], A[tri(i, cc)]);
+            const int rem = m - j - 1;  // trailing rows j+1 .. m-1; their lower triangle, flat over all threads
+            for (int t = threadIdx.x; t < rem * (rem + 1) / 2; t += THREADS) {
+                int r, c;
+                tri_rc(t, r, c);
+                const int i = j + 1 + r, cc = j + 1 + c;
+                if (cc < n) A[tri(i, cc)] = dd_fnma(A[tri(i, j)], A[tri(cc, j)], A[tri(i, cc)]);  // cc >= n: rhs x rhs, unused
             }
         }
         __syncthreads();
@@ -216,16 +234,17 @@ cudaError_t launch_rescue(const NllArgs& a, int mode, cudaStream_t st, long long
     }
     dd* ws = nullptr;
     if (e == cudaSuccess) {
-        const size_t fixed = 2 * KMAX * sizeof(double), mat = rescue_elems(a.n) * sizeof(dd);
+        const size_t fixed = 3 * KMAX * sizeof(double), mat = rescue_elems(a.n) * sizeof(dd);
+        const bool rowmajor = !nll_uses_flow(a.n, a.k);  // the dataflow kernel's tables are tile-packed: recompute the powers there
         if (fixed + mat <= smem_optin()) {
             const size_t smem = fixed + mat;
             int per_sm = (int)((228 * 1024) / (smem + 1024));
-            if (per_sm > 4) per_sm = 4;
+            if (per_sm > 5) per_sm = 5;  // 48 registers x 256 threads: five CTAs fit the register file
             long long grid = (long long)sm_count() * per_sm;
             if (grid > a.C) grid = a.C;
             e = cudaFuncSetAttribute(krig_rescue_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e == cudaSuccess) {
-                krig_rescue_kernel<256><<<(int)grid, 256, smem, st>>>(a, mode, list, cnt, nullptr, 0, fo);
+                krig_rescue_kernel<256><<<(int)grid, 256, smem, st>>>(a, mode, list, cnt, nullptr, 0, fo, rowmajor);
                 e = cudaGetLastError();
             }
         } else {  // matrix in a per-CTA slice of global memory (L2-resident up to n ~ 2000)
@@ -236,7 +255,7 @@ cudaError_t launch_rescue(const NllArgs& a, int mode, cudaStream_t st, long long
             if (grid > a.C) grid = a.C;
             e = cudaMallocAsync((void**)&ws, (size_t)grid * mat, st);
             if (e == cudaSuccess) {
-                krig_rescue_kernel<1024><<<(int)grid, 1024, fixed, st>>>(a, mode, list, cnt, ws, rescue_elems(a.n), fo);
+                krig_rescue_kernel<1024><<<(int)grid, 1024, fixed, st>>>(a, mode, list, cnt, ws, rescue_elems(a.n), fo, rowmajor);
                 e = cudaGetLastError();
             }
         }

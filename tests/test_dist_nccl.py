@@ -31,21 +31,26 @@ def _worker(rank, world, port, q):
         shard, bv2, bi2 = k.likelihood_batch(e, p, return_best=True)
         mine = k.likelihood_batch(e, p, gather=False)
         lo, hi = 1001 * rank // world, 1001 * (rank + 1) // world
-        ok = np.array_equal(full, shard, equal_nan=True) and (bv1, bi1) == (bv2, bi2) and np.isnan(shard[17])
-        ok = ok and np.array_equal(mine, full[lo:hi], equal_nan=True)
+        ok = {}
+        ok['list nll'] = np.array_equal(full, shard, equal_nan=True) and bool(np.isnan(shard[17]))
+        ok['list argmin'] = (bv1, bi1) == (bv2, bi2)
+        ok['list local slice'] = np.array_equal(mine, full[lo:hi], equal_nan=True)
         param, idx = k.grid_search(4, 2)                               # 4^4 * 2^4 = 4096 candidates over 2 ranks
         param1, idx1 = k.grid_search(4, 2, distributed=False)
-        ok = ok and idx == idx1 and param == param1
+        ok['grid'] = idx == idx1 and param == param1
         k.update_param(10. ** e[3], p[3])
         xq = np.random.default_rng(5).uniform(0, 1, (3001, 4))
         y1, m1 = k.predict_batch(xq, return_mse=True, distributed=False)
         y2, m2 = k.predict_batch(xq, return_mse=True)
-        ok = ok and np.array_equal(y1, y2) and np.array_equal(m1, m2)
-        ok = ok and np.array_equal(k.predict_batch(xq, gather=False), y1[3001 * rank // world:3001 * (rank + 1) // world])
+        ok['predict mse'] = np.array_equal(y1, y2) and np.array_equal(m1, m2)
+        y3 = k.predict_batch(xq, distributed=False)
+        ok['predict mean slice'] = np.array_equal(k.predict_batch(xq, gather=False), y3[3001 * rank // world:3001 * (rank + 1) // world])
+        ok['predict mean'] = np.array_equal(k.predict_batch(xq), y3)
         r = RBF(X, y)
         r.update_param(1.0, 'gaus')
-        ok = ok and np.array_equal(r.predict_batch(xq), r.predict_batch(xq, distributed=False))
-        q.put((rank, bool(ok), int(bi2)))
+        ok['rbf'] = np.array_equal(r.predict_batch(xq), r.predict_batch(xq, distributed=False))
+        bad = [name for name, v in ok.items() if not v]
+        q.put((rank, bad, int(bi2)))
     finally:
         td.destroy_process_group()
 
@@ -65,4 +70,5 @@ def test_two_rank_sharded_likelihood_and_prediction():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert all(ok for _, ok, _ in res) and res[0][2] == res[1][2]
+    assert all(not bad for _, bad, _ in res), res
+    assert res[0][2] == res[1][2]

@@ -10,6 +10,7 @@ from mylibs.kriging import Kriging  # noqa: E402
 from sm_b200 import workloads  # noqa: E402
 
 count = int(sys.argv[1]) if len(sys.argv) > 1 else 200000
+begin = int(sys.argv[3]) if len(sys.argv) > 3 else 400000
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 if n == 64:
     X, y = workloads.c2_halton64()
@@ -18,11 +19,11 @@ else:
     X = X * 10
 k = Kriging(X, y)
 for _ in range(2):
-    bv, bi, _ = k.likelihood_grid(40, 25, 400000, count, return_nll=True)
+    bv, bi, _ = k.likelihood_grid(40, 25, begin, count, return_nll=True)
 torch.cuda.synchronize()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record()
-bv, bi, _ = k.likelihood_grid(40, 25, 400000, count, return_nll=True)
+bv, bi, _ = k.likelihood_grid(40, 25, begin, count, return_nll=True)
 b.record()
 torch.cuda.synchronize()
 print(f'n={n} count={count} best {bv} @ {bi}: {a.elapsed_time(b):.3f} ms -> {count / a.elapsed_time(b) * 1e3:.4g} evals/s')
