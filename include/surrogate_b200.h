@@ -69,6 +69,17 @@ int sm_krig_nll_grid_host(const double* X, const double* y, int n, int k, const 
                           const double* p_axis, int P, int64_t c_begin, int64_t c_count, double* nll_out,
                           double* best_val, int64_t* best_idx);
 
+/* ---- leave-one-out batch (PRESS) ---------------------------------------------------------------------
+ * The grid stage of re-training one surrogate per left-out sample, as Validation.calc_press intends it
+ * (mylibs/validation.py:79-110: `sur = surro_class(x, fx); sur.train()` inside `for i in range(len(known_x))`; the
+ * reference's np.delete(x, 0, ...) always drops sample 0 -- see the host mirror's quirk switch): sample set m = the n
+ * samples without sample m, m = 0..n-1, each searched over the same T^k * P^k grid as sm_krig_nll_grid.  For n - 1 <= 144,
+ * k <= 8 all n * T^k * P^k (sample set, candidate) pairs run in ONE launch of the likelihood kernel (model index = flat
+ * index / grid size).  nll_out[n][T^k P^k] may be NULL; best_val[n] / best_idx[n]: first minimum per sample set, index
+ * local to its grid (-1 if none finite).  All pointers are device pointers except the two axes' sizes. */
+int sm_krig_loo_grid(const double* X, const double* y, int n, int k, const double* theta_axis, int T, const double* p_axis,
+                     int P, double* nll_out, double* best_val, int64_t* best_idx, void* stream);
+
 /* ---- batched likelihood over an explicit candidate list -------------------------------------------
  * Replaces a Python loop of Kriging.update_param(theta_c, p_c) + calc_likelihood()
  * (mylibs/kriging.py:53-63, 95-116; e.g. examples/kriging_r2.py:91-97).  theta[C][k] linear, p[C][k].

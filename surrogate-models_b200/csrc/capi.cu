@@ -145,6 +145,59 @@ int sm_krig_nll_grid(const double* X, const double* y, int n, int k, const doubl
     return 0;
 }
 
+int sm_krig_loo_grid(const double* X, const double* y, int n, int k, const double* theta_axis, int T, const double* p_axis,
+                     int P, double* nll_out, double* best_val, int64_t* best_idx, void* stream) {
+    if (!X || !y || !theta_axis || !p_axis || !best_val || !best_idx || bad_nk(n, k) || n < 2 || T < 1 || P < 1) return SM_E_BADARG;
+    keep_pool_cached();
+    cudaStream_t st = (cudaStream_t)stream;
+    Launches L;
+    const int n1 = n - 1, npad = sm_krig_npad(n1);
+    long long gt = 1;
+    for (int d = 0; d < k; ++d) {
+        gt *= (long long)T * P;
+        if (gt > ((long long)1 << 40)) return SM_E_TOOBIG;
+    }
+    DevBuf xm(st), ym(st), nll_tmp(st);
+    SM_TRY(xm.alloc((size_t)n * n1 * k * 8));
+    SM_TRY(ym.alloc((size_t)n * n1 * 8));
+    SM_TRY(launch_loo_gather(X, y, n, k, xm.as<double>(), ym.as<double>(), st));
+    L.n += 1;
+    if (!nll_out) {
+        SM_TRY(nll_tmp.alloc((size_t)n * gt * 8));
+        nll_out = nll_tmp.as<double>();
+    }
+    const size_t dstride = (size_t)npad * npad * k * P;
+    // one launch over (sample set, candidate) when the warp-per-candidate kernel takes the size; else one grid call per set
+    if (!nll_uses_flow(n1, k) && k <= 8 && npad <= 144 && dstride * n * 8 <= ((size_t)1 << 30)) {
+        DevBuf dtab(st), egrid(st);
+        SM_TRY(dtab.alloc(dstride * n * 8));
+        SM_TRY(launch_dtab(xm.as<double>(), n1, k, npad, p_axis, P, dtab.as<double>(), st, n));
+        L.n += 1;
+        NllArgs a{};
+        a.X = xm.as<double>(); a.y = ym.as<double>(); a.n = n1; a.k = k; a.npad = npad;
+        a.C = (long long)n * gt; a.c_begin = 0;
+        a.theta_axis = theta_axis; a.T = T; a.P = P; a.p_axis = p_axis; a.dtab = dtab.as<double>();
+        a.models = n; a.grid_total = gt; a.y_stride = (size_t)n1; a.dtab_model_stride = dstride;
+        a.nll_out = nll_out;
+        const size_t estride = dstride * T;
+        if (npad <= 96 && k <= 4 && estride * n * 8 <= ((size_t)256 << 20)) {
+            SM_TRY(egrid.alloc(estride * n * 8));
+            SM_TRY(launch_egrid(dtab.as<double>(), theta_axis, k * n, P, T, npad, egrid.as<double>(), st));
+            L.n += 1;
+            a.egrid = egrid.as<double>();
+            a.egrid_model_stride = estride;
+        }
+        SM_TRY(launch_nll(a, 0, st, &L.n));
+    } else {
+        for (int m = 0; m < n; ++m)
+            SM_TRY((cudaError_t)sm_krig_nll_grid(xm.as<double>() + (size_t)m * n1 * k, ym.as<double>() + (size_t)m * n1, n1, k, theta_axis, T,
+                                                 p_axis, P, 0, gt, nll_out + (size_t)m * gt, nullptr, nullptr, stream));
+    }
+    SM_TRY(launch_argmin_segments(nll_out, gt, n, best_val, (long long*)best_idx, st));
+    L.n += 1;
+    return 0;
+}
+
 int sm_krig_nll_batch(const double* X, const double* y, int n, int k, const double* theta, const double* p,
                       int64_t C, int64_t idx_base, double* nll_out, double* best_val, int64_t* best_idx,
                       void* stream) {

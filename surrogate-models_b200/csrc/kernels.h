@@ -25,6 +25,12 @@ struct NllArgs {
     const double* p;      // [C][k]
     const double* logtab;  // [k][npad][npad]  ln|dx| (n <= 128 kernels)
     const double* log2tab;  // [k][npad][npad]  512 log2|dx| (krig_nll_flow.cu, n > 128)
+    // model dimension (leave-one-out / PRESS, grid mode of the warp-per-candidate kernel only): candidate c belongs to model
+    // c / grid_total and is grid candidate c % grid_total of it; model m reads X + m n k, y + m y_stride and the tables
+    // dtab + m dtab_model_stride / egrid + m egrid_model_stride.  models <= 1: the plain single-model call.
+    int models;
+    long long grid_total;
+    size_t y_stride, dtab_model_stride, egrid_model_stride;
     // output / scratch
     double* nll_out;    // [C]
     double* workspace;  // tile storage for the global-memory variant
@@ -62,7 +68,10 @@ cudaError_t launch_log2tab(const double* X, int n, int k, int npad, double* LG, 
 cudaError_t launch_dtab_packed(const double* X, int n, int k, int npad, const double* p_axis, int P, double* D, cudaStream_t st);
 size_t flow_table_doubles(int n);  // doubles of ONE tile-packed lower-triangle table
 size_t flow_workspace_doubles(int n);  // doubles of one candidate's workspace: (4 NB + 1) tile rows of NT tiles
-cudaError_t launch_dtab(const double* X, int n, int k, int npad, const double* p_axis, int P, double* D, cudaStream_t st);
+cudaError_t launch_dtab(const double* X, int n, int k, int npad, const double* p_axis, int P, double* D, cudaStream_t st,
+                        int models = 1);
+cudaError_t launch_loo_gather(const double* X, const double* y, int n, int k, double* Xm, double* ym, cudaStream_t st);
+cudaError_t launch_argmin_segments(const double* v, long long seg, int nseg, double* best_val, long long* best_idx, cudaStream_t st);
 cudaError_t launch_egrid(const double* dtab, const double* theta_axis, int k, int P, int T, int npad, double* E, cudaStream_t st);
 cudaError_t launch_logtab(const double* X, int n, int k, int npad, double* LG, cudaStream_t st);
 cudaError_t launch_argmin(const double* v, long long C, long long c_begin, double* best_val, long long* best_idx,

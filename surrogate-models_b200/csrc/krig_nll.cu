@@ -27,6 +27,8 @@ __global__ void dtab_kernel(const double* __restrict__ X, int n, int k, int npad
                             const double* __restrict__ p_axis, int P, double* __restrict__ D) {
     const size_t per = (size_t)npad * npad;
     const size_t total = per * k * P;
+    X += (size_t)blockIdx.y * n * k;  // blockIdx.y: sample set of a leave-one-out batch (0 for the plain call)
+    D += (size_t)blockIdx.y * total;
     for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
         const int j = (int)(t % npad);
         const int i = (int)((t / npad) % npad);
@@ -371,11 +373,49 @@ static cudaError_t launch_nll_fp64(NllArgs a, int mode, cudaStream_t st, long lo
     return e;
 }
 
-cudaError_t launch_dtab(const double* X, int n, int k, int npad, const double* p_axis, int P, double* D, cudaStream_t st) {
+cudaError_t launch_dtab(const double* X, int n, int k, int npad, const double* p_axis, int P, double* D, cudaStream_t st,
+                        int models) {
     const size_t total = (size_t)npad * npad * k * P;
     int grid = (int)((total + 255) / 256);
     if (grid > 148 * 16) grid = 148 * 16;
-    dtab_kernel<<<grid, 256, 0, st>>>(X, n, k, npad, p_axis, P, D);
+    dtab_kernel<<<dim3(grid, models), 256, 0, st>>>(X, n, k, npad, p_axis, P, D);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------ leave-one-out sample sets
+// Xm[m][r][:] = X[r + (r >= m)][:], ym[m][r] = y[r + (r >= m)]: sample set m is the data without sample m
+__global__ void loo_gather_kernel(const double* __restrict__ X, const double* __restrict__ y, int n, int k,
+                                  double* __restrict__ Xm, double* __restrict__ ym) {
+    const int m = blockIdx.y, n1 = n - 1;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n1 * k; t += gridDim.x * blockDim.x) {
+        const int r = t / k, d = t % k;
+        const int src = r + (r >= m);
+        Xm[((size_t)m * n1 + r) * k + d] = X[(size_t)src * k + d];
+        if (d == 0) ym[(size_t)m * n1 + r] = y[src];
+    }
+}
+cudaError_t launch_loo_gather(const double* X, const double* y, int n, int k, double* Xm, double* ym, cudaStream_t st) {
+    loo_gather_kernel<<<dim3(((n - 1) * k + 255) / 256, n), 256, 0, st>>>(X, y, n, k, Xm, ym);
+    return cudaGetLastError();
+}
+// first minimum of every segment of `seg` values (one CTA per segment; index local to the segment, -1 if none finite)
+__global__ void __launch_bounds__(256) argmin_segments_kernel(const double* __restrict__ v, long long seg, double* best_val,
+                                                              long long* best_idx) {
+    __shared__ MinIdx sh[8];
+    const double* s = v + (size_t)blockIdx.x * seg;
+    MinIdx m{INFINITY, -1};
+    for (long long c = threadIdx.x; c < seg; c += blockDim.x) {
+        const double x = s[c];
+        if (x < m.v) m = MinIdx{x, c};
+    }
+    m = block_min_first(m, sh);
+    if (threadIdx.x == 0) {
+        best_val[blockIdx.x] = m.v;
+        best_idx[blockIdx.x] = m.i;
+    }
+}
+cudaError_t launch_argmin_segments(const double* v, long long seg, int nseg, double* best_val, long long* best_idx, cudaStream_t st) {
+    argmin_segments_kernel<<<nseg, 256, 0, st>>>(v, seg, best_val, best_idx);
     return cudaGetLastError();
 }
 cudaError_t launch_egrid(const double* dtab, const double* theta_axis, int k, int P, int T, int npad, double* E, cudaStream_t st) {

@@ -254,11 +254,16 @@ krig_nll_small_kernel(const NllArgs a) {
     for (long long c = first; c < a.C; c += stride) {
         // ---------------------------------------------------------------- candidate parameters
         SmallParams<KD> P;
+        long long model = 0;
         if (MODE == 0 || MODE == 2) {
             // flat index -> per-dimension digits (dimension 0 the fastest).  32-bit arithmetic whenever the index and
             // the digit spaces fit (always, for k <= 4 grids): the 64-bit divisions of the first version were 2 500 of
             // the 7 500 instructions per candidate (ncu source page, capture h)
-            const long long cg = a.c_begin + c;
+            long long cg = a.c_begin + c;
+            if (a.models > 1) {  // leave-one-out batch: which sample set, which grid candidate of it
+                model = cg / a.grid_total;
+                cg -= model * a.grid_total;
+            }
             unsigned dt[KD], dp[KD];
             if (fast_decode && cg < 0xffffffffll) {
                 const unsigned cu = (unsigned)cg;
@@ -294,10 +299,10 @@ krig_nll_small_kernel(const NllArgs a) {
                 const int dd = (d < a.k) ? d : a.k - 1;  // KD > k (the KD = 8 instantiation for k = 5..7): weight 0
                 if (MODE == 0) {
                     P.th[d] = (d < a.k) ? a.theta_axis[dt[d]] : 0.0;
-                    P.tab[d] = a.dtab + ((long long)dd * a.P + dp[d]) * per;
+                    P.tab[d] = a.dtab + model * a.dtab_model_stride + ((long long)dd * a.P + dp[d]) * per;
                 } else {
                     P.th[d] = 0.0;
-                    P.tab[d] = a.egrid + (((long long)dd * a.P + dp[d]) * a.T + dt[d]) * per;
+                    P.tab[d] = a.egrid + model * a.egrid_model_stride + (((long long)dd * a.P + dp[d]) * a.T + dt[d]) * per;
                 }
             }
         } else {
@@ -404,8 +409,14 @@ krig_nll_small_kernel(const NllArgs a) {
             }
             {
                 const int j0 = 8 * J + 2 * q;
-                const double y0 = (r == 0) ? y_s[j0] : ((r == 1 && j0 < a.n) ? 1.0 : 0.0);
-                const double y1 = (r == 0) ? y_s[j0 + 1] : ((r == 1 && j0 + 1 < a.n) ? 1.0 : 0.0);
+                double yv0 = y_s[j0], yv1 = y_s[j0 + 1];
+                if (a.models > 1) {  // per-model responses: from global memory (L1-resident, two loads per block column)
+                    const double* ym = a.y + model * a.y_stride;
+                    yv0 = (j0 < a.n) ? __ldg(ym + j0) : 0.0;
+                    yv1 = (j0 + 1 < a.n) ? __ldg(ym + j0 + 1) : 0.0;
+                }
+                const double y0 = (r == 0) ? yv0 : ((r == 1 && j0 < a.n) ? 1.0 : 0.0);
+                const double y1 = (r == 0) ? yv1 : ((r == 1 && j0 + 1 < a.n) ? 1.0 : 0.0);
                 if (r < 2) {
                     rhs_s[J * 16 + r * 8 + 2 * q] = y0 - accr[0];
                     rhs_s[J * 16 + r * 8 + 2 * q + 1] = y1 - accr[1];

@@ -74,20 +74,25 @@ __global__ void __launch_bounds__(THREADS) krig_rescue_kernel(const NllArgs a, c
 
     for (unsigned long long it = blockIdx.x; it < total; it += gridDim.x) {
         const long long c = list[it];
+        const size_t model = (mode == 0 && a.models > 1) ? (size_t)((a.c_begin + c) / a.grid_total) : 0;
+        const double* Xm = a.X + model * (size_t)n * k;
+        const double* ym = a.y + model * a.y_stride;
         __syncthreads();  // previous candidate done with th / pw / A
         if (threadIdx.x < k) {
             const int d = threadIdx.x;
             if (mode == 0) {  // grid: flat index -> digits, dimension 0 the fastest (likeli_optimizer.py:89-97)
                 long long tk = 1;
                 for (int e = 0; e < k; ++e) tk *= a.T;
-                long long cg = a.c_begin + c, ti = cg % tk, pi = cg / tk;
+                long long cg = a.c_begin + c;
+                if (a.models > 1) cg %= a.grid_total;
+                long long ti = cg % tk, pi = cg / tk;
                 for (int e = 0; e < d; ++e) {
                     ti /= a.T;
                     pi /= a.P;
                 }
                 th[d] = a.theta_axis[ti % a.T];
                 pw[d] = a.p_axis[pi % a.P];
-                toff[d] = ((size_t)d * a.P + (size_t)(pi % a.P)) * a.npad * a.npad;
+                toff[d] = model * a.dtab_model_stride + ((size_t)d * a.P + (size_t)(pi % a.P)) * a.npad * a.npad;
             } else {
                 th[d] = a.theta[c * k + d];
                 pw[d] = a.p[c * k + d];
@@ -108,12 +113,12 @@ __global__ void __launch_bounds__(THREADS) krig_rescue_kernel(const NllArgs a, c
                 for (int d = 0; d < k; ++d) s = __dadd_rn(s, __dmul_rn(th[d], a.dtab[toff[d] + (size_t)i * a.npad + j]));
             } else {
                 for (int d = 0; d < k; ++d)
-                    s = __dadd_rn(s, __dmul_rn(th[d], pow_cr(fabs(a.X[(size_t)i * k + d] - a.X[(size_t)j * k + d]), pw[d])));
+                    s = __dadd_rn(s, __dmul_rn(th[d], pow_cr(fabs(Xm[(size_t)i * k + d] - Xm[(size_t)j * k + d]), pw[d])));
             }
             A[t] = dd{exp_cr(-s), 0.0};
         }
         for (int j = threadIdx.x; j < n; j += THREADS) {
-            A[tri(n, j)] = dd{a.y[j], 0.0};
+            A[tri(n, j)] = dd{ym[j], 0.0};
             A[tri(n + 1, j)] = dd{1.0, 0.0};
         }
         // ---- right-looking Cholesky of the leading n x n block, carried through the two right-hand-side rows

@@ -404,6 +404,9 @@ class Kriging:
         NCCL; every rank returns the same (best_param, best_idx[, local nll])."""
         T, P = int(theta_sections), int(p_sections)
         total = (T ** self._k) * (P ** self._k)
+        seeded = getattr(self, '_grid_guess', None)
+        if seeded is not None and (T, P) in seeded and not return_nll:   # set by a leave-one-out batch (loo_grid_guesses)
+            return seeded[(T, P)]
         rank, world = dist.rank_world(distributed)
         lo, hi = dist.shard_range(total, rank, world)
         bv_d, bi_d, nll = self.likelihood_grid(T, P, lo, hi - lo, return_nll=return_nll, as_device=True)
@@ -412,6 +415,27 @@ class Kriging:
         if return_nll:
             return param, bi, nll.cpu().numpy()
         return param, bi
+
+    def loo_grid_guesses(self, theta_sections=8, p_sections=5, return_nll=False):
+        """Grid stage of re-training one model per left-out sample (PRESS, validation.py:79-110) as ONE batched launch
+        over (sample set, candidate) pairs -- sm_krig_loo_grid.  Returns a list of n (best_param, best_idx) pairs: entry m
+        is what Kriging(X without sample m, y without sample m).grid_search(...) returns."""
+        L = _cabi.lib()
+        d = self._dev()
+        T, P = int(theta_sections), int(p_sections)
+        total = (T ** self._k) * (P ** self._k)
+        th_axis, p_axis = grid_axes(T, P)
+        th_lin = device.to_dev(np.array([10.**e for e in th_axis]))
+        pa = device.to_dev(p_axis)
+        nll = device.empty((self._n, total)) if return_nll else None
+        bv, bi = device.empty(self._n), device.empty(self._n, dtype=_int64())
+        _cabi.check(L.sm_krig_loo_grid(device.ptr(d['X']), device.ptr(d['y']), self._n, self._k, device.ptr(th_lin), T,
+                                       device.ptr(pa), P, device.ptr(nll), device.ptr(bv), device.ptr(bi), device.stream()))
+        idx = bi.cpu().numpy()
+        out = [(None if c < 0 else grid_param(self._k, T, P, int(c)), int(c)) for c in idx]
+        if return_nll:
+            return out, nll.cpu().numpy()
+        return out
 
     def predict_batch(self, x_query, return_mse=False, distributed=None, gather=True):
         """Mean (and ordinary-Kriging MSE) at many query points: Xq[Nq,k] -> y[Nq] (, mse[Nq]).

@@ -49,18 +49,21 @@ class Validation:
         vali_fx = np.asarray(vali_fx, dtype=np.float64)
         return abs(np.divide((vali_fx - _predict_all(surro_func, vali_x)), vali_fx))
 
-    def calc_press(self, known_x, known_fx, surro_func, surro_class, update_params=None):
+    def calc_press(self, known_x, known_fx, surro_func, surro_class, update_params=None, quirk=True):
         """prediction sum of squares (reference: validation.py:79-110).
 
-        Quirk preserved: the reference re-trains a surrogate for every i but ALWAYS leaves out sample 0
-        (np.delete(x, 0, axis=0), validation.py:92,94), i.e. it trains the same model n times.  That model
+        quirk=True (default, the reference's behaviour): the reference re-trains a surrogate for every i but ALWAYS leaves
+        out sample 0 (np.delete(x, 0, axis=0), validation.py:92,94), i.e. it trains the same model n times.  That model
         is built once here and evaluated at all n points in one batch -- the returned value is the same.
-        Any exception while building it gives the reference's warning and 0."""
+        quirk=False: true leave-one-out -- model i is trained without sample i and evaluated at sample i.  For the B200
+        Kriging class the grid stage of all n trainings is ONE batched launch (Kriging.loo_grid_guesses, n sample sets x
+        1600 candidates); the SLSQP refinements and the n predictions follow per model.
+        Any exception while building a model gives the reference's warning and 0."""
         n = len(known_x)
         res = _predict_all(surro_func, known_x)
-        x = np.delete(np.array(known_x), 0, axis=0)
-        fx = np.delete(np.array(known_fx), 0, axis=0)
-        try:
+        x_all, fx_all = np.array(known_x), np.array(known_fx)
+
+        def build(x, fx, seed_guess=None):
             sur = surro_class(x, fx)
             if update_params is not None:
                 if len(update_params) == 1:
@@ -69,11 +72,26 @@ class Validation:
                     sur.update_param(update_params[0], update_params[1])
                 else:
                     print('Validation.calc_press please update to support more params than 2')
+            if seed_guess is not None:
+                sur._grid_guess = {(8, 5): seed_guess}   # the grid of LikeliOptimizer.find (likeli_optimizer.py:36)
             sur.train()
+            return sur
+
+        try:
+            if quirk:
+                sur = build(np.delete(x_all, 0, axis=0), np.delete(fx_all, 0, axis=0))
+                res2 = _predict_all(sur.predict, known_x)
+            else:
+                guesses = [None] * n
+                if hasattr(surro_class, 'loo_grid_guesses'):
+                    guesses = surro_class(x_all, fx_all).loo_grid_guesses(8, 5)
+                res2 = np.empty(n)
+                for i in range(n):
+                    sur = build(np.delete(x_all, i, axis=0), np.delete(fx_all, i, axis=0), guesses[i])
+                    res2[i] = sur.predict(known_x[i])
         except Exception as e:
             print('WARNING: missing train() method: ' + str(e))
             return 0.
-        res2 = _predict_all(sur.predict, known_x)
         return math.sqrt(float(np.sum((res - res2) ** 2.)) / n)
 
     def run_full_analysis(self, params, values, known_x, known_fx, vali_x, vali_fx, surro_func, surro_class,

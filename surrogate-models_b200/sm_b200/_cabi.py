@@ -27,6 +27,7 @@ SIGNATURES = {
     'sm_krig_rescue_stats': (_i, [_vp, _vp, _i]),
     'sm_krig_nll_grid': (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _i, _i64, _i64, _vp, _vp, _vp, _vp]),
     'sm_krig_nll_grid_host': (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _i, _i64, _i64, _vp, _vp, _vp]),
+    'sm_krig_loo_grid': (_i, [_vp, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     'sm_krig_nll_batch': (_i, [_vp, _vp, _i, _i, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     'sm_krig_nll_batch_host': (_i, [_vp, _vp, _i, _i, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     'sm_krig_fit': (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

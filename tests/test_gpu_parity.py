@@ -1064,3 +1064,58 @@ def test_mean_prediction_beyond_one_shared_memory_stage(K):
     f = orc.fit_chol(X, y, th, p)
     ref = orc.predict_chol(X, y, th, p, xq, False)
     assert rel(k._fit['mu'], f['mu']) < 1e-9 and np.max(rel(got, ref)) < 1e-8
+
+
+# ------------------------------------------------------------------------------------------ PRESS / leave-one-out batch
+def test_leave_one_out_grid_batch_and_press(gold, K, R_, capsys):
+    """sm_krig_loo_grid evaluates n sample sets x 1600 candidates in one launch -- every row equals
+    the single-model grid of that sample set; Validation.calc_press(quirk=False) is the true leave-one-out built on it,
+    quirk=True keeps the reference's always-delete-sample-0 value (reference fixture)."""
+    from mylibs.validation import Validation
+    g = gold('c5_kriging_r3')
+    X, y = g['X'], g['y']
+    k = K(X, y)
+    n0 = _cabi.launch_count()
+    guesses, nll = k.loo_grid_guesses(8, 5, return_nll=True)
+    assert _cabi.launch_count() - n0 <= 8 and nll.shape == (36, 1600)
+    for m in (0, 7, 35):
+        km = K(np.delete(X, m, axis=0), np.delete(y, m))
+        param, idx, ref = km.grid_search(8, 5, return_nll=True)
+        assert np.array_equal(nll[m], ref, equal_nan=True) and guesses[m] == (param, idx)
+        lu = np.array([orc.nll_opti_exp(np.delete(X, m, axis=0), np.delete(y, m), np.concatenate([e, q]), 'lu')
+                       for e, q in zip(*orc.grid_candidates(2, 8, 5, 0, 1600))][::40])
+        cond = np.array([orc.cond2(orc.corr_matrix(np.delete(X, m, axis=0), 10. ** e, q))
+                         for e, q in zip(*orc.grid_candidates(2, 8, 5, 0, 1600))][::40])
+        check_values(nll[m][::40], lu, cond)
+    # n = 64, k = 2 (egrid tables too large for 64 sets -> plain tables), and a size beyond the one-launch path
+    g2 = gold('c2_halton64_default_grid')
+    k2 = K(g2['X'], g2['y_fb'])
+    gs2 = k2.loo_grid_guesses(8, 5)
+    assert gs2[5] == K(np.delete(g2['X'], 5, axis=0), np.delete(g2['y_fb'], 5)).grid_search(8, 5)
+    rng = np.random.default_rng(2)
+    Xb = rng.uniform(0, 10, (150, 2))
+    yb = np.sin(Xb.sum(axis=1))
+    gb = K(Xb, yb).loo_grid_guesses(3, 2)
+    assert gb[149] == K(Xb[:149], yb[:149]).grid_search(3, 2)
+    # PRESS through the validation protocol
+    v = Validation()
+    gv = gold('validation_r3')
+    r = R_(X, y)
+    r.update_param(1.0, 'gaus')
+    assert rel(v.calc_press(X, y, r.predict, R_, update_params=[1.0, 'gaus']), gv['rbf_press']) < 1e-8   # reference value
+    kf = K(X, y)
+    kf.update_param([0.05, 0.05], [1.9, 1.9])
+    press = v.calc_press(X, y, kf.predict, K, quirk=False)
+    capsys.readouterr()
+    # true leave-one-out by hand on three of the models (grid + SLSQP per model, like train())
+    for i in (0, 17):
+        ki = K(np.delete(X, i, axis=0), np.delete(y, i))
+        ki.train()
+        kj = K(np.delete(X, i, axis=0), np.delete(y, i))
+        kj._grid_guess = {(8, 5): guesses[i]}
+        kj.train()
+        assert np.array_equal(ki._theta, kj._theta) and np.array_equal(ki._p, kj._p)
+    capsys.readouterr()
+    assert np.isfinite(press) and press > 0
+    pq = v.calc_press(X, y, kf.predict, K, quirk=True)
+    assert np.isfinite(pq) and pq != press
