@@ -61,6 +61,7 @@ NllPlan plan_nll(int n);
 size_t nll_smem_bytes(int npad, int slots, int nwarps, size_t tile_bytes);
 cudaError_t launch_nll(NllArgs a, int mode, cudaStream_t st, long long* launches);
 cudaError_t launch_nll_small(const NllArgs& a, int mode, cudaStream_t st);
+cudaError_t launch_nll_n64(const NllArgs& a, int mode, cudaStream_t st);
 cudaError_t launch_nll_large(NllArgs a, int mode, cudaStream_t st);
 cudaError_t launch_nll_flow(NllArgs a, int mode, cudaStream_t st);
 bool nll_uses_flow(int n, int k);

@@ -19,7 +19,8 @@ from myutils.time_track import TimeTrack
 from sm_b200 import _cabi, device, dist
 
 VERBOSE = False
-LAZY_FIT_MIN_N = 145  # from here on the optimiser objective is one single-candidate launch of the batched kernel
+import os
+LAZY_FIT_MIN_N = int(os.environ.get('SMB_LAZY_FIT_MIN_N', '145'))  # from here on the optimiser objective is one single-candidate launch of the batched kernel
 
 
 class Kriging:
