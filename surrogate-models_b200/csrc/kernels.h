@@ -18,6 +18,7 @@ struct NllArgs {
     const double* theta_axis;
     int T, P;
     const double* p_axis;  // [P] (grid mode; read by the extended-precision rescue pass only)
+    int tab_layout;      // 0: row-major [npad][npad] tables; 1: tile-packed (dataflow kernel); 2: tile64 (register-resident npad = 64 kernel)
     const double* dtab;  // [k][P][npad][npad]
     const double* egrid;  // optional [k][P][T][npad][npad]: exp(-theta_axis[t] * dtab) -- product-form entries
     // list mode (MODE 1)
@@ -62,6 +63,11 @@ size_t nll_smem_bytes(int npad, int slots, int nwarps, size_t tile_bytes);
 cudaError_t launch_nll(NllArgs a, int mode, cudaStream_t st, long long* launches);
 cudaError_t launch_nll_small(const NllArgs& a, int mode, cudaStream_t st);
 cudaError_t launch_nll_n64(const NllArgs& a, int mode, cudaStream_t st);
+cudaError_t launch_nll_n64r(const NllArgs& a, int mode, cudaStream_t st);
+// true when the register-resident npad = 64 kernel takes (n, k): its tables use the tile64 layout (TILE64_PER doubles per
+// table instead of npad^2; launch_dtab / launch_logtab / launch_egrid build it when called with npad = 0)
+bool nll_uses_n64r(int n, int k);
+constexpr int TILE64_PER = 36 * 64;
 cudaError_t launch_nll_large(NllArgs a, int mode, cudaStream_t st);
 cudaError_t launch_nll_flow(NllArgs a, int mode, cudaStream_t st);
 bool nll_uses_flow(int n, int k);

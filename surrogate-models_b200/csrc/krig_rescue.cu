@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(THREADS) krig_rescue_kernel(const NllArgs a, c
     double* pw = th + KMAX;                        // [KMAX]
     size_t* toff = reinterpret_cast<size_t*>(pw + KMAX);  // [KMAX] offset of table (d, q_d) in a.dtab
     dd* A = ws_stride ? gws + (size_t)blockIdx.x * ws_stride : reinterpret_cast<dd*>(toff + KMAX);
-    const bool tabbed = (mode == 0) && a.dtab != nullptr && tab_rowmajor;
+    const bool tabbed = (mode == 0) && a.dtab != nullptr && tab_rowmajor;  // layout 0 (row-major) or 2 (tile64)
+    const size_t tper = (a.tab_layout == 2) ? (size_t)TILE64_PER : (size_t)a.npad * a.npad;
     const int n = a.n, k = a.k, m = n + 2;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned long long total = *cnt;
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(THREADS) krig_rescue_kernel(const NllArgs a, c
                 }
                 th[d] = a.theta_axis[ti % a.T];
                 pw[d] = a.p_axis[pi % a.P];
-                toff[d] = model * a.dtab_model_stride + ((size_t)d * a.P + (size_t)(pi % a.P)) * a.npad * a.npad;
+                toff[d] = model * a.dtab_model_stride + ((size_t)d * a.P + (size_t)(pi % a.P)) * tper;
             } else {
                 th[d] = a.theta[c * k + d];
                 pw[d] = a.p[c * k + d];
@@ -110,7 +111,11 @@ __global__ void __launch_bounds__(THREADS) krig_rescue_kernel(const NllArgs a, c
             tri_rc(t, i, j);
             double s = 0.0;
             if (tabbed) {  // grid mode, row-major |dx|^p tables (built with the same correctly rounded pow)
-                for (int d = 0; d < k; ++d) s = __dadd_rn(s, __dmul_rn(th[d], a.dtab[toff[d] + (size_t)i * a.npad + j]));
+                // element (i, j), i >= j: row-major, or tile64 (tile (i/8, j/8), lane (i%8, j%4), slot (j%8)/4)
+                const size_t eoff = (a.tab_layout == 2)
+                    ? (size_t)(((i >> 3) * ((i >> 3) + 1) / 2 + (j >> 3)) * 64 + 2 * (4 * (i & 7) + (j & 3)) + ((j & 7) >> 2))
+                    : (size_t)i * a.npad + j;
+                for (int d = 0; d < k; ++d) s = __dadd_rn(s, __dmul_rn(th[d], a.dtab[toff[d] + eoff]));
             } else {
                 for (int d = 0; d < k; ++d)
                     s = __dadd_rn(s, __dmul_rn(th[d], pow_cr(fabs(Xm[(size_t)i * k + d] - Xm[(size_t)j * k + d]), pw[d])));
@@ -240,7 +245,7 @@ cudaError_t launch_rescue(const NllArgs& a, int mode, cudaStream_t st, long long
     dd* ws = nullptr;
     if (e == cudaSuccess) {
         const size_t fixed = 3 * KMAX * sizeof(double), mat = rescue_elems(a.n) * sizeof(dd);
-        const bool rowmajor = !nll_uses_flow(a.n, a.k);  // the dataflow kernel's tables are tile-packed: recompute the powers there
+        const bool rowmajor = a.tab_layout != 1;  // the dataflow kernel's tables are tile-packed: recompute the powers there
         if (fixed + mat <= smem_optin()) {
             const size_t smem = fixed + mat;
             int per_sm = (int)((228 * 1024) / (smem + 1024));
