@@ -108,6 +108,58 @@ class RBF:
             y = dist.gather_slices(y, nq)
         return y.cpu().numpy()
 
+    # ------------------------------------------------------------------ batch over the rbf constant (additive)
+    def sweep_rbf_const(self, a_values, x_query, rbf_name='gaus'):
+        """Predictions of the surrogate at x_query for EVERY rbf constant in a_values: one weight solve + one evaluation
+        per constant, enqueued back to back on the stream with a single synchronisation at the end -- the batched form of
+        the loop `update_param(a, name); predict(x)` that Surrogate.auto_fit_rbf drives through SLSQP
+        (wingconstruction/surrogate_run.py:146-166).  Returns pred[len(a_values), Nq]; a singular system gives a NaN row.
+        The object's own parameters are left untouched."""
+        import torch
+        L = _cabi.lib()
+        d = self._dev()
+        kind = _KIND[_NAMES.get(rbf_name, gaus_rbf)]
+        xq = np.asarray(x_query, dtype=np.float64)
+        if xq.ndim == 1:
+            xq = xq.reshape(-1, self._k)
+        xq_d = device.to_dev(xq)
+        a_values = [float(a) for a in a_values]
+        pred = device.empty((len(a_values), xq.shape[0]))
+        coeff = device.empty((len(a_values), self._n))
+        info = torch.zeros(len(a_values), dtype=torch.int32, device=pred.device)
+        for i, a in enumerate(a_values):
+            _cabi.check(L.sm_rbf_fit(device.ptr(d['X']), device.ptr(d['y']), self._n, self._k, kind, a,
+                                     coeff[i].data_ptr(), info[i:].data_ptr(), device.stream()))
+            _cabi.check(L.sm_rbf_predict(device.ptr(d['X']), self._n, self._k, kind, a, coeff[i].data_ptr(),
+                                         device.ptr(xq_d), xq.shape[0], pred[i].data_ptr(), device.stream()))
+        out = pred.cpu().numpy()
+        out[info.cpu().numpy() > 0] = np.nan
+        return out
+
+    def auto_fit(self, vali_x, vali_fx, rbf_name='gaus', init_a=1., bounds=(0.01, 5.), grid=48, scale=1.):
+        """The search of Surrogate.auto_fit_rbf (surrogate_run.py:146-166: SLSQP over the rbf constant a in [0.01, 5],
+        objective = validation RMSE / scale) with the B200 batch in front: the RMSE over a `grid`-point sweep of a comes
+        from ONE sweep_rbf_const call, SLSQP (same settings as the reference) then starts from the better of the sweep's
+        minimum and init_a.  Leaves the model trained at the optimum and returns (a, rmse / scale)."""
+        from scipy.optimize import minimize
+        vali_x = np.asarray(vali_x, dtype=np.float64)
+        vali_fx = np.asarray(vali_fx, dtype=np.float64)
+
+        def objective(a):
+            self.update_param(float(np.atleast_1d(a)[0]), rbf_name)
+            err = vali_fx - self.predict_batch(vali_x)
+            return math.sqrt(float(np.sum(err ** 2)) / len(vali_x)) / scale
+        cand = np.concatenate([[init_a], np.linspace(bounds[0], bounds[1], grid)])
+        sweep = self.sweep_rbf_const(cand, vali_x, rbf_name)
+        rmse = np.sqrt(np.sum((vali_fx[None, :] - sweep) ** 2, axis=1) / len(vali_x)) / scale
+        start = float(cand[int(np.nanargmin(rmse))])
+        res = minimize(objective, start, method='SLSQP', tol=1e-8, options={'disp': False, 'maxiter': 999}, bounds=[bounds])
+        best = float(res.x[0])
+        if not (res.fun <= np.nanmin(rmse)):  # SLSQP may end worse than its start (the reference keeps res.x regardless)
+            best = start
+        self.update_param(best, rbf_name)
+        return best, objective(best)
+
     def predict_device(self, xq_dev):
         if self._coeff is None:
             raise TypeError("'NoneType' object is not subscriptable (predict before update_param)")
@@ -145,3 +197,5 @@ def inv_multi_quad_rbf(a, r):
 
 
 _KIND = {lin_rbf: 0, cubic_rbf: 1, gaus_rbf: 2, multi_quad_rbf: 3, inv_multi_quad_rbf: 4}
+_NAMES = {'lin': lin_rbf, 'cubic': cubic_rbf, 'gaus': gaus_rbf, 'multi-quadratic': multi_quad_rbf, 'mq': multi_quad_rbf,
+          'inverse-multi-quadratic': inv_multi_quad_rbf, 'imq': inv_multi_quad_rbf}

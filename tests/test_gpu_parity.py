@@ -1119,3 +1119,85 @@ def test_leave_one_out_grid_batch_and_press(gold, K, R_, capsys):
     assert np.isfinite(press) and press > 0
     pq = v.calc_press(X, y, kf.predict, K, quirk=True)
     assert np.isfinite(pq) and pq != press
+
+
+# ------------------------------------------------------------------------------------------ SURVEY 8(f) rank 3
+def test_rbf_constant_sweep_and_auto_fit(gold, R_):
+    """The a-sweep behind auto_fit_rbf (wingconstruction/surrogate_run.py:146-166) as one batch: every row equals the
+    reference-shaped loop update_param(a, name) + predict, for a definite and a non-definite kernel; auto_fit ends at (or
+    below) the best sweep point."""
+    g = gold('rbf_r3_all_kernels')
+    X, y, xq = g['X'], g['y'], g['xq']
+    r = R_(X, y)
+    a_vals = [0.17, 0.5, 1.0, 1.3, 2.5]
+    for name in ('gaus', 'mq'):
+        sweep = r.sweep_rbf_const(a_vals, xq, name)
+        for i, a in enumerate(a_vals):
+            coeff = orc.rbf_fit(X, y, orc.RBF_KINDS[name], a)
+            ref = orc.rbf_predict(X, coeff, orc.RBF_KINDS[name], a, xq)
+            c = orc.cond2(orc.rbf_matrix(X, orc.RBF_KINDS[name], a))
+            assert np.max(rel(sweep[i], ref)) < 1e-9 * max(1.0, c / 1e6), (name, a, c)
+    assert np.max(rel(r.sweep_rbf_const([1.0], xq, 'gaus')[0], g['pred_gaus'])) < 1e-9          # reference fixture
+    rng = np.random.default_rng(4)
+    vx = rng.uniform(0, 10, (60, 2))
+    from myutils.samples import f_3d
+    vy = np.array([f_3d(v) for v in vx])
+    a_best, score = r.auto_fit(vx, vy, 'gaus')
+    grid = np.linspace(0.01, 5., 48)
+    sw = r.sweep_rbf_const(grid, vx, 'gaus')
+    rm = np.sqrt(np.sum((vy[None, :] - sw) ** 2, axis=1) / len(vx))
+    assert 0.01 <= a_best <= 5. and score <= np.nanmin(rm) * (1 + 1e-9)
+    assert r._rbf_const == a_best and rel(r.predict(vx[0]), r.predict_batch(vx[:1])[0]) < 1e-15
+
+
+def test_likelihood_surface_plot_routes(gold, K, monkeypatch):
+    """plot_theta_likelihood_r2 / plot_p_likelihood_r2 / plot_likelihoods (reference kriging.py:222-327) without matplotlib:
+    a recording stand-in for PlotHelper captures what would be drawn; the 50 x 50 surfaces must equal the reference's
+    loop of update_param + calc_likelihood (oracle, LU form) point by point."""
+    import sys
+    import types
+    g = gold('c5_kriging_r3')
+    X, y = g['X'], g['y']
+    drawn = []
+
+    class Ax:
+        def set_xscale(self, *a): pass
+        def set_yscale(self, *a): pass
+        def plot(self, *a, **k): pass
+        def pcolor(self, xs, ys, z, cmap=None):
+            drawn.append((np.array(xs), np.array(ys), np.array(z)))
+            return types.SimpleNamespace(get_array=lambda z=z: np.asarray(z), set_clim=lambda *a: None)
+
+    class FakePlotHelper:
+        def __init__(self, labels, fancy=False, ax=None, pgf=False):
+            self.ax = ax if ax is not None else Ax()
+            self.fig = types.SimpleNamespace(add_subplot=lambda *a: Ax(), set_size_inches=lambda *a: None, colorbar=lambda *a: None)
+        def finalize(self, **kw): pass
+
+    import myutils.plot_helper as ph
+    monkeypatch.setattr(ph, 'PlotHelper', FakePlotHelper)
+    plt = types.ModuleType('matplotlib.pyplot')
+    plt.figure = lambda: types.SimpleNamespace(add_subplot=lambda *a: Ax(), set_size_inches=lambda *a: None, colorbar=lambda *a: None)
+    monkeypatch.setitem(sys.modules, 'matplotlib', types.ModuleType('matplotlib'))
+    monkeypatch.setitem(sys.modules, 'matplotlib.pyplot', plt)
+    k = K(X, y)
+    k.update_param([0.05, 0.07], [1.9, 1.4])
+    k.plot_theta_likelihood_r2()
+    thetas, _, surf = drawn[-1]
+    assert surf.shape == (50, 50) and np.allclose(thetas, np.logspace(-5, 5, 50))
+    for i1, i2 in ((10, 20), (25, 25), (30, 12), (22, 40)):       # likely_thet[i2][i1] = nll(theta1 = thetas[i1], theta2 = thetas[i2])
+        ref = orc.nll_lu(X, y, [thetas[i1], thetas[i2]], [1.9, 1.4])
+        c = orc.cond2(orc.corr_matrix(X, [thetas[i1], thetas[i2]], [1.9, 1.4]))
+        if c < 1e8:
+            assert rel(surf[i2][i1], ref) < tol(c), (i1, i2, c)
+    k.plot_p_likelihood_r2()
+    ps, _, surf_p = drawn[-1]
+    assert np.allclose(ps, np.linspace(1, 2, 50))
+    ref = orc.nll_lu(X, y, [0.05, 0.07], [ps[7], ps[33]])
+    assert rel(surf_p[33][7], ref) < 1e-9
+    assert list(k._theta) == [0.05, 0.07] and list(k._p) == [1.9, 1.4]          # the sweeps leave the model alone
+    n_before = len(drawn)
+    k.plot_likelihoods(opti_path=np.array([[-1., -1., 1.5, 1.5], [-2., -1.5, 1.7, 1.2]]))
+    assert len(drawn) == n_before + 2
+    k1 = K(X[:, :1], y)
+    assert k1.plot_theta_likelihood_r2() is None                                   # only for exactly 2 inputs
