@@ -292,6 +292,150 @@ __global__ void __launch_bounds__(256) lu_update_kernel(double* __restrict__ A, 
         for (int i = threadIdx.x; i < m; i += blockDim.x) rhs[c + 1 + i] = fma(-l[i], rhs[c], rhs[c + 1 + i]);
 }
 
+// ------------------------------------------------------------------------------------ blocked LU (n > 64)
+// Right-looking LU with partial pivoting in panels of LU_NB columns (what LAPACK's getrf does for np.linalg.solve,
+// mylibs/rbf.py:79): panel factorisation on one CTA, row swaps + unit-lower triangular solve of the U12 block, trailing update
+// A22 -= L21 U12 on DMMA.  Three launches per panel instead of two per column (n = 4096: 384 instead of 8 192).  The
+// right-hand side is forward-substituted inside the panel kernel, so the columns left of a panel are never touched again.
+constexpr int LU_NB = 32;
+
+__global__ void __launch_bounds__(1024) lu_panel_kernel(double* __restrict__ A, double* __restrict__ rhs, int n, int c0, int nbw,
+                                                        int* __restrict__ piv, int* __restrict__ info) {
+    __shared__ double bv[32];
+    __shared__ int bi[32];
+    __shared__ int piv_s;
+    for (int j = 0; j < nbw; ++j) {
+        const int c = c0 + j;
+        double* col = A + (size_t)c * n;
+        double best = -1.0;
+        int besti = c;
+        for (int i = c + threadIdx.x; i < n; i += blockDim.x) {
+            const double v = fabs(col[i]);
+            if (v > best) { best = v; besti = i; }  // first maximum per thread (increasing i)
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+            if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+        }
+        if ((threadIdx.x & 31) == 0) { bv[threadIdx.x >> 5] = best; bi[threadIdx.x >> 5] = besti; }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            best = (threadIdx.x < (blockDim.x >> 5)) ? bv[threadIdx.x] : -1.0;
+            besti = (threadIdx.x < (blockDim.x >> 5)) ? bi[threadIdx.x] : n;
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+                if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+            }
+            if (threadIdx.x == 0) {
+                piv_s = besti;
+                piv[c] = besti;
+                if (!(best > 0.0) && *info == 0) *info = c + 1;  // exactly singular (LAPACK info > 0)
+            }
+        }
+        __syncthreads();
+        const int p = piv_s;
+        if (p != c) {  // swap rows c and p inside the panel, and in the right-hand side
+            if (threadIdx.x < nbw) {
+                double* cj = A + (size_t)(c0 + threadIdx.x) * n;
+                const double t = cj[c];
+                cj[c] = cj[p];
+                cj[p] = t;
+            }
+            if (threadIdx.x == 32) { const double t = rhs[c]; rhs[c] = rhs[p]; rhs[p] = t; }
+        }
+        __syncthreads();
+        const double d = 1.0 / col[c];
+        const double rc = rhs[c];
+        __syncthreads();  // col[c], rhs[c] read by everyone before the scaling / update below rewrites anything
+        const int m = n - c - 1, w = nbw - j - 1;
+        for (int i = threadIdx.x; i < m; i += blockDim.x) {
+            const double l = col[c + 1 + i] * d;
+            col[c + 1 + i] = l;
+            rhs[c + 1 + i] = fma(-l, rc, rhs[c + 1 + i]);
+        }
+        __syncthreads();
+        for (size_t t = threadIdx.x; t < (size_t)m * w; t += blockDim.x) {  // remaining panel columns
+            const int i = (int)(t % m), jj = (int)(t / m);
+            double* cj = A + (size_t)(c + 1 + jj) * n;
+            cj[c + 1 + i] = fma(-col[c + 1 + i], cj[c], cj[c + 1 + i]);
+        }
+        __syncthreads();
+    }
+}
+
+// columns right of the panel: the panel's row swaps, then U12 = L11^-1 A12 (unit lower L11, one column per thread)
+__global__ void __launch_bounds__(256) lu_swap_trsm_kernel(double* __restrict__ A, int n, int c0, int nbw, const int* __restrict__ piv) {
+    __shared__ double L11[LU_NB * LU_NB];
+    __shared__ int pv[LU_NB];
+    for (int t = threadIdx.x; t < nbw * nbw; t += blockDim.x) L11[t] = A[(size_t)(c0 + t / nbw) * n + c0 + t % nbw];  // [col][row]
+    if (threadIdx.x < nbw) pv[threadIdx.x] = piv[c0 + threadIdx.x];
+    __syncthreads();
+    const int jc = c0 + nbw + blockIdx.x * blockDim.x + threadIdx.x;
+    if (jc >= n) return;
+    double* col = A + (size_t)jc * n;
+    for (int j = 0; j < nbw; ++j) {
+        const int p = pv[j];
+        if (p != c0 + j) { const double t = col[c0 + j]; col[c0 + j] = col[p]; col[p] = t; }
+    }
+    double u[LU_NB];
+#pragma unroll
+    for (int j = 0; j < LU_NB; ++j) u[j] = (j < nbw) ? col[c0 + j] : 0.0;
+#pragma unroll
+    for (int j = 0; j < LU_NB; ++j)
+#pragma unroll
+        for (int jj = j + 1; jj < LU_NB; ++jj)
+            if (jj < nbw) u[jj] = fma(-L11[j * nbw + jj], u[j], u[jj]);
+#pragma unroll
+    for (int j = 0; j < LU_NB; ++j)
+        if (j < nbw) col[c0 + j] = u[j];
+}
+
+// A22 -= L21 U12: CTA tile 64 x 64, operands staged in shared memory, 8 warps x (4 x 2) DMMA tiles
+__global__ void __launch_bounds__(256) lu_gemm_kernel(double* __restrict__ A, int n, int c0, int nbw) {
+    constexpr int AS = 72, BS = 36;           // padded strides: As[k][row], Bs[col][k]
+    __shared__ double As[LU_NB * AS], Bs[64 * BS];
+    const int r0 = c0 + nbw + blockIdx.x * 64, j0 = c0 + nbw + blockIdx.y * 64;
+    for (int t = threadIdx.x; t < LU_NB * 64; t += blockDim.x) {
+        const int kk = t >> 6, i = t & 63;
+        As[kk * AS + i] = (kk < nbw && r0 + i < n) ? A[(size_t)(c0 + kk) * n + r0 + i] : 0.0;
+    }
+    for (int t = threadIdx.x; t < 64 * LU_NB; t += blockDim.x) {
+        const int jj = t >> 5, kk = t & 31;
+        Bs[jj * BS + kk] = (kk < nbw && j0 + jj < n) ? A[(size_t)(j0 + jj) * n + c0 + kk] : 0.0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int r = lane >> 2, q = lane & 3;
+    const int wr = (wid & 1) * 32, wc = (wid >> 1) * 16;
+    double acc[4][2][2];
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) acc[t][u][0] = acc[t][u][1] = 0.0;
+#pragma unroll
+    for (int kq = 0; kq < LU_NB / 4; ++kq) {
+        double af[4], bf[2];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) af[t] = As[(4 * kq + q) * AS + wr + 8 * t + r];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) bf[u] = Bs[(wc + 8 * u + r) * BS + 4 * kq + q];
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int u = 0; u < 2; ++u) dmma(acc[t][u][0], acc[t][u][1], af[t], bf[u]);
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int i = r0 + wr + 8 * t + r, j = j0 + wc + 8 * u + 2 * q;
+            if (i < n && j < n) A[(size_t)j * n + i] -= acc[t][u][0];
+            if (i < n && j + 1 < n) A[(size_t)(j + 1) * n + i] -= acc[t][u][1];
+        }
+}
+
 // U x = z, single CTA, column oriented
 __global__ void __launch_bounds__(1024) lu_backsolve_kernel(const double* __restrict__ A, double* __restrict__ rhs, int n) {
     __shared__ double xj;
@@ -358,17 +502,35 @@ cudaError_t launch_rbf_fit(const double* X, const double* y, int n, int k, int k
     rbf_matrix_kernel<<<grid, 256, 0, st>>>(X, n, k, kind, a, A);
     e = cudaMemcpyAsync(coeff, y, (size_t)n * 8, cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return e;
-    for (int c = 0; c < n; ++c) {
-        lu_pivot_kernel<<<1, n - c > 2048 ? 1024 : 256, 0, st>>>(A, coeff, n, c, info);
-        const int m = n - c - 1;
-        if (m > 0) {
-            int g = (int)(((size_t)m * m + 255) / 256);
-            if (g > 148 * 8) g = 148 * 8;
-            lu_update_kernel<<<g, 256, 0, st>>>(A, coeff, n, c);
+    if (n > 64) {  // blocked
+        int* piv = nullptr;
+        e = cudaMallocAsync((void**)&piv, (size_t)n * sizeof(int), st);
+        if (e != cudaSuccess) return e;
+        for (int c0 = 0; c0 < n; c0 += LU_NB) {
+            const int nbw = n - c0 < LU_NB ? n - c0 : LU_NB;
+            lu_panel_kernel<<<1, n - c0 > 512 ? 1024 : 256, 0, st>>>(A, coeff, n, c0, nbw, piv, info);
+            const int rest = n - c0 - nbw;
+            if (rest > 0) {
+                lu_swap_trsm_kernel<<<(rest + 255) / 256, 256, 0, st>>>(A, n, c0, nbw, piv);
+                lu_gemm_kernel<<<dim3((rest + 63) / 64, (rest + 63) / 64), 256, 0, st>>>(A, n, c0, nbw);
+            }
+            if (launches) *launches += rest > 0 ? 3 : 1;
         }
+        cudaFreeAsync(piv, st);
+    } else {
+        for (int c = 0; c < n; ++c) {
+            lu_pivot_kernel<<<1, 256, 0, st>>>(A, coeff, n, c, info);
+            const int m = n - c - 1;
+            if (m > 0) {
+                int g = (int)(((size_t)m * m + 255) / 256);
+                if (g > 148 * 8) g = 148 * 8;
+                lu_update_kernel<<<g, 256, 0, st>>>(A, coeff, n, c);
+            }
+        }
+        if (launches) *launches += 2 * (long long)n;
     }
     lu_backsolve_kernel<<<1, n > 2048 ? 1024 : 256, 0, st>>>(A, coeff, n);
-    if (launches) *launches += 2 * (long long)n + 2;
+    if (launches) *launches += 2;
     e = cudaGetLastError();
     cudaError_t e2 = cudaFreeAsync(A, st);
     return e != cudaSuccess ? e : e2;

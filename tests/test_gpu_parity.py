@@ -1201,3 +1201,25 @@ def test_likelihood_surface_plot_routes(gold, K, monkeypatch):
     assert len(drawn) == n_before + 2
     k1 = K(X[:, :1], y)
     assert k1.plot_theta_likelihood_r2() is None                                   # only for exactly 2 inputs
+
+
+@pytest.mark.parametrize('n,name,a', [(65, 'mq', 0.7), (100, 'lin', 1.0), (257, 'cubic', 1.0), (520, 'mq', 0.5), (1000, 'imq', 1.3)])
+def test_rbf_blocked_lu_ragged_sizes(R_, n, name, a):
+    """non-definite kernels, n > 64: blocked LU with partial pivoting (panels of 32, DMMA trailing update) against
+    np.linalg.solve through the oracle; sizes straddling the panel / tile boundaries"""
+    rng = np.random.default_rng(n)
+    X = rng.uniform(0, 10, (n, 3))
+    y = np.sin(X[:, 0]) + 0.05 * X[:, 1] ** 2 - 0.01 * X[:, 2] ** 3
+    r = R_(X, y)
+    r.update_param(a, name)
+    kind = orc.RBF_KINDS[name]
+    Phi = orc.rbf_matrix(X, kind, a)
+    c = orc.cond2(Phi)
+    coeff = r.get_coeff()
+    # backward error of the solve (what partial pivoting guarantees), and agreement with numpy where conditioning allows
+    resid = np.max(np.abs(Phi @ coeff - y)) / (np.max(np.abs(Phi)) * np.max(np.abs(coeff)) * n)
+    assert resid < 1e-14, resid
+    ref = orc.rbf_fit(X, y, kind, a)
+    assert np.max(np.abs(coeff - ref)) <= 1e-13 * c * np.max(np.abs(ref)) + 1e-12, (c, np.max(np.abs(coeff - ref)))
+    xq = rng.uniform(0, 10, (20, 3))
+    assert np.max(rel(r.predict_batch(xq), orc.rbf_predict(X, ref, kind, a, xq))) < 1e-9 * max(1.0, c / 1e6)
