@@ -91,9 +91,15 @@ __device__ __forceinline__ bool diag_factor_fill_r(double c0, double c1, double*
     return ok;
 }
 
+// one shared copy of the 8-step diagonal factor (no filler): used with -DN64R_SHARED_DIAG to measure what the 8 inlined,
+// filler-carrying copies cost in instruction-cache traffic
+__device__ __noinline__ bool diag_factor_shared(double c0, double c1, double* ts, double* wt, double& tp, int lane, double tau) {
+    return diag_factor(c0, c1, ts, wt, tp, lane, tau);
+}
+
 #ifndef N64R_WARPS
 #define N64R_WARPS 4   // warps per CTA
-#define N64R_MINB 3    // CTAs per SM: 12 warps, 168 registers per thread
+#define N64R_MINB 3    // CTAs per SM: 12 warps, 168 registers per thread (8 warps x 254 registers: -1 %, 16 x 128 with spills: +4 %)
 #endif
 
 template <int KD, int MODE, int WARPS, int MINB>
@@ -302,6 +308,16 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) krig_nll_n64r_kernel(const N
             constexpr bool halves = (2 * ksteps <= 8) && ncnt >= 2;
             constexpr int hsplit = (ncnt + 1) / 2;
             using JN = std::integral_constant<int, (J < 7 ? J + 1 : 7)>;
+#ifdef N64R_SHARED_DIAG
+            if constexpr (ksteps > 0) {
+                sfor<ksteps>([&](auto Kc) {
+                    constexpr int K = decltype(Kc)::value;
+                    kstep(JN{}, std::integral_constant<int, (K < 7 ? K : 0)>{}, I0{}, std::integral_constant<int, (ncnt > 0 ? ncnt : 1)>{}, TrueT{});
+                });
+            }
+            (void)halves; (void)hsplit;
+            ok = diag_factor_shared(dc0, dc1, dscr, wscr, tp, lane, tau) && ok;
+#else
             ok = diag_factor_fill_r(dc0, dc1, dscr, wscr, tp, lane, tau, [&](auto Sc) {
                 constexpr int s = decltype(Sc)::value;
                 if constexpr (halves) {   // two pivot steps per k-step: tiles [0, hsplit) | [hsplit, ncnt) + rhs
@@ -315,6 +331,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) krig_nll_n64r_kernel(const N
                     kstep(JN{}, std::integral_constant<int, (s < 7 ? s : 0)>{}, I0{}, std::integral_constant<int, (ncnt > 0 ? ncnt : 1)>{}, TrueT{});
                 }
             }) && ok;
+#endif
             if (lane == J) prod = tp;
             // ------------------------------------------------------------ T: L_IJ = C_IJ W^T, W's rows permuted -> operand fragments
             if constexpr (J < 7) load_tab(JN{}, I0{}, std::integral_constant<int, (ncnt < 4 ? ncnt : 4)>{});
