@@ -42,6 +42,13 @@ int sm_b200_version(void);
 const char* sm_b200_error_string(int code);
 /* kernels launched by this library since load (bench.py's gpu_launches) */
 long long sm_b200_launch_count(void);
+/* Scratch (tables, tile workspaces) comes from the device's default stream-ordered memory pool, which keeps up to
+ * SMB_POOL_KEEP_MB (environment, default 2048) cached between calls; sm_b200_trim_pool() synchronises the device and
+ * returns all cached scratch to the driver. */
+int sm_b200_trim_pool(void);
+/* theta = 10 ** e element-wise, correctly rounded -- the reference forms theta with libm's pow(10., e)
+ * (Kriging._calc_likelihood_opti_exp, mylibs/kriging.py:133-136); device pointers */
+int sm_exp10(const double* e, int64_t count, double* out, void* stream);
 /* padded size (multiple of 8) and number of doubles of the packed L^-1 operand tiles for n samples */
 int sm_krig_npad(int n);
 size_t sm_krig_mop_doubles(int n);

@@ -1,6 +1,7 @@
 // extern "C" boundary (include/surrogate_b200.h): argument checks, table set-up, kernel launches and the
 // host-buffer wrappers.  No torch types, no CPU arithmetic.
 #include <atomic>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/surrogate_b200.h"
@@ -41,7 +42,11 @@ void keep_pool_cached() {
     if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        unsigned long long thr = ~0ull;
+        // keep up to SMB_POOL_KEEP_MB (default 2048) of freed scratch cached in the pool; anything above goes back to the
+        // driver at the next synchronisation, so a caching allocator next door (PyTorch) is not starved.
+        // sm_b200_trim_pool() releases the rest on demand.
+        unsigned long long thr = 2048ull << 20;
+        if (const char* v = getenv("SMB_POOL_KEEP_MB")) thr = (unsigned long long)atoll(v) << 20;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
     done_for = dev;
@@ -84,6 +89,15 @@ const char* sm_b200_error_string(int code) {
     if (code == SM_E_BADARG) return "surrogate_b200: bad argument";
     if (code == SM_E_TOOBIG) return "surrogate_b200: problem exceeds kernel capacity";
     return cudaGetErrorString((cudaError_t)code);
+}
+int sm_b200_trim_pool(void) {
+    int dev = 0;
+    SM_TRY(cudaGetDevice(&dev));
+    cudaMemPool_t pool;
+    SM_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
+    SM_TRY(cudaDeviceSynchronize());
+    SM_TRY(cudaMemPoolTrimTo(pool, 0));
+    return 0;
 }
 int sm_krig_npad(int n) { return (n + 7) / 8 * 8; }
 double sm_krig_pivot_tau(void) { return SMB_PIVOT_TAU; }
@@ -145,6 +159,13 @@ int sm_krig_nll_grid(const double* X, const double* y, int n, int k, const doubl
         SM_TRY(launch_argmin(nll_out, c_count, c_begin, best_val, (long long*)best_idx, st));
         L.n += 2;
     }
+    return 0;
+}
+
+int sm_exp10(const double* e, int64_t count, double* out, void* stream) {
+    if (!e || !out || count < 0) return SM_E_BADARG;
+    Launches L;
+    SM_TRY(launch_exp10_cr(e, count, out, (cudaStream_t)stream, &L.n));
     return 0;
 }
 

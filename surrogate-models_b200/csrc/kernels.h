@@ -98,6 +98,7 @@ size_t fit_tile_doubles(int n);
 // also rewrites mu, sigma2, info, w, b, rres from the double-double factorisation)
 cudaError_t launch_rescue(const NllArgs& a, int mode, cudaStream_t st, long long* launches, const FitOut* fit = nullptr);
 cudaError_t rescue_stats(unsigned long long* out, int reset);
+cudaError_t launch_exp10_cr(const double* e, long long count, double* out, cudaStream_t st, long long* launches);
 // weights-only fit for the sizes of the dataflow kernel (n >= 113 by default; no Mop): dataflow kernel on one candidate + back-substitution on the kept factor
 cudaError_t launch_krig_fit_weights(const double* X, const double* y, int n, int k, const double* theta, const double* p,
                                     FitOut out, cudaStream_t st, long long* launches);

@@ -844,7 +844,12 @@ static cudaError_t launch_flow_t(NllArgs a, int mode, cudaStream_t st) {
     if (per_sm > CPS) per_sm = CPS;
     long long grid = (long long)sm_count() * per_sm;
     if (grid > a.C) grid = a.C;
-    const long long ws_cap = (long long)(((size_t)24 << 30) / tile_bytes);
+    // workspace: one factor per resident CTA, sized from what the device has free right now (half of it, at most 24 GB)
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = (size_t)48 << 30;
+    size_t ws_budget = free_b / 2;
+    if (ws_budget > ((size_t)24 << 30)) ws_budget = (size_t)24 << 30;
+    const long long ws_cap = (long long)(ws_budget / tile_bytes);
     if (grid > ws_cap) grid = ws_cap > 0 ? ws_cap : 1;
     if (a.workspace) {  // caller-owned workspace of ONE candidate (single-model fit keeps the factor)
         if (a.C != 1) return cudaErrorInvalidValue;

@@ -345,7 +345,10 @@ class Kriging:
             return (np.empty(0), float('inf'), -1) if return_best else np.empty(0)
         rank, world = dist.rank_world(distributed)
         lo, hi = dist.shard_range(C, rank, world)
-        nll_d, bv_d, bi_d = self._likelihood_list_dev(np.power(10., e[lo:hi]), q[lo:hi], lo)  # 10.**e, vectorised
+        e_d = device.to_dev(e[lo:hi])
+        th_d = device.empty(e_d.shape)  # theta = 10.**e on the device, correctly rounded like the reference's scalar pow
+        _cabi.check(_cabi.lib().sm_exp10(device.ptr(e_d), e_d.numel(), device.ptr(th_d), device.stream()))
+        nll_d, bv_d, bi_d = self._likelihood_list_dev(th_d, q[lo:hi], lo)
         if world > 1:
             bv, bi = dist.global_first_min_dev(bv_d, bi_d) if return_best else (None, None)
             if gather:

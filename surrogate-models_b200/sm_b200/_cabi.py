@@ -21,6 +21,8 @@ SIGNATURES = {
     'sm_b200_version': (_i, []),
     'sm_b200_error_string': (ctypes.c_char_p, [_i]),
     'sm_b200_launch_count': (ctypes.c_longlong, []),
+    'sm_b200_trim_pool': (_i, []),
+    'sm_exp10': (_i, [_vp, _i64, _vp, _vp]),
     'sm_krig_npad': (_i, [_i]),
     'sm_krig_mop_doubles': (ctypes.c_size_t, [_i]),
     'sm_krig_pivot_tau': (_d, []),

@@ -1223,3 +1223,21 @@ def test_rbf_blocked_lu_ragged_sizes(R_, n, name, a):
     assert np.max(np.abs(coeff - ref)) <= 1e-13 * c * np.max(np.abs(ref)) + 1e-12, (c, np.max(np.abs(coeff - ref)))
     xq = rng.uniform(0, 10, (20, 3))
     assert np.max(rel(r.predict_batch(xq), orc.rbf_predict(X, ref, kind, a, xq))) < 1e-9 * max(1.0, c / 1e6)
+
+
+def test_device_exp10_matches_scalar_pow_and_pool_trim(K):
+    """sm_exp10 (theta = 10 ** e for list-mode candidates) against Python's scalar pow -- the reference's 10.**e
+    (kriging.py:133-136); numpy's vectorised power is off by an ulp in ~5 % of the cases.  sm_b200_trim_pool returns 0."""
+    from sm_b200 import device
+    rng = np.random.default_rng(0)
+    e = np.concatenate([rng.uniform(-5, 5, 200000), np.linspace(-5, 5, 40), [0., 1., -1., 3.]])
+    ed = device.to_dev(e)
+    out = device.empty(e.shape)
+    _cabi.check(_cabi.lib().sm_exp10(device.ptr(ed), e.size, device.ptr(out), device.stream()))
+    got = out.cpu().numpy()
+    want = np.array([10. ** v for v in e])
+    mism = int((got != want).sum())
+    assert mism <= 2e-3 * e.size, mism                     # glibc's own pow is misrounded in ~8e-4 of the calls
+    assert np.max(np.abs(got - want) / want) < 3e-16
+    assert int((np.power(10., e) != want).sum()) > 10 * max(mism, 1)
+    assert _cabi.lib().sm_b200_trim_pool() == 0
