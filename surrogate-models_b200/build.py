@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIBDIR, 'libsurrogate_b200.so')
-SOURCES = ['capi.cu', 'krig_nll.cu', 'krig_nll_small.cu', 'krig_nll_small8.cu', 'krig_nll_n64.cu', 'krig_nll_n64r.cu', 'krig_nll_large.cu', 'krig_nll_flow.cu', 'krig_fit.cu', 'krig_rescue.cu', 'krig_predict.cu', 'rbf.cu']
+SOURCES = ['capi.cu', 'krig_nll.cu', 'krig_nll_small.cu', 'krig_nll_small8.cu', 'krig_nll_n64.cu', 'krig_nll_large.cu', 'krig_nll_flow.cu', 'krig_fit.cu', 'krig_rescue.cu', 'krig_predict.cu', 'rbf.cu']
 NVCC_FLAGS = ([f'-D{d}' for d in os.environ.get('SMB_DEFINES', '').split(',') if d]) + ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC']
 
@@ -32,13 +32,17 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
     objs = []
     procs = []
-    for src in SOURCES:
-        obj = os.path.join(LIBDIR, src.replace('.cu', '.o'))
+    # the register-resident likelihood kernel is statically unrolled per matrix size: one translation unit per NT = npad / 8
+    units = [(src, [], src.replace('.cu', '.o')) for src in SOURCES]
+    units += [('krig_nll_regs.cu', [f'-DSMB_REGS_NT={nt}'], f'krig_nll_regs_{nt}.o') for nt in (10, 9, 8, 7, 6, 5)]
+    units.sort(key=lambda u: 0 if u[0] == 'krig_nll_regs.cu' else 1)  # the slowest units first
+    for src, defs, objname in units:
+        obj = os.path.join(LIBDIR, objname)
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, '-c', os.path.join(CSRC, src), '-o', obj]
+        cmd = [nvcc, *NVCC_FLAGS, *defs, '-c', os.path.join(CSRC, src), '-o', obj]
         if verbose:
             cmd.insert(1, '-Xptxas=-v')
-        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        procs.append((objname, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
         out, _ = p.communicate()
         if p.returncode != 0:

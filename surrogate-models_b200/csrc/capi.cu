@@ -124,14 +124,14 @@ int sm_krig_nll_grid(const double* X, const double* y, int n, int k, const doubl
     const int npad = sm_krig_npad(n);
     DevBuf dtab(st), nll_tmp(st);
     const bool flow = nll_uses_flow(n, k);  // tile-packed lower-triangle tables for the dataflow kernel
-    const bool t64 = nll_uses_n64r(n, k);   // tile64 tables for the register-resident npad = 64 kernel
-    const size_t tper = t64 ? (size_t)TILE64_PER : (size_t)npad * npad;
+    const bool t64 = nll_uses_regs(n, k);   // packed-fragment tables for the register-resident kernels
+    const size_t tper = t64 ? regs_table_doubles(npad) : (size_t)npad * npad;
     if (flow) {
         SM_TRY(dtab.alloc(flow_table_doubles(n) * k * P * 8));
         SM_TRY(launch_dtab_packed(X, n, k, npad, p_axis, P, dtab.as<double>(), st));
     } else {
         SM_TRY(dtab.alloc(tper * k * P * 8));
-        SM_TRY(launch_dtab(X, n, k, t64 ? 0 : npad, p_axis, P, dtab.as<double>(), st));
+        SM_TRY(launch_dtab(X, n, k, t64 ? -npad : npad, p_axis, P, dtab.as<double>(), st));
     }
     L.n += 1;
     if (!nll_out) {
@@ -150,7 +150,7 @@ int sm_krig_nll_grid(const double* X, const double* y, int n, int k, const doubl
     const size_t egrid_bytes = tper * k * P * T * 8;
     if (!flow && npad <= 96 && k <= 4 && egrid_bytes <= ((size_t)256 << 20)) {
         SM_TRY(egrid.alloc(egrid_bytes));
-        SM_TRY(launch_egrid(dtab.as<double>(), theta_axis, k, P, T, t64 ? 0 : npad, egrid.as<double>(), st));
+        SM_TRY(launch_egrid(dtab.as<double>(), theta_axis, k, P, T, t64 ? -npad : npad, egrid.as<double>(), st));
         L.n += 1;
         a.egrid = egrid.as<double>();
     }
@@ -190,13 +190,13 @@ int sm_krig_loo_grid(const double* X, const double* y, int n, int k, const doubl
         SM_TRY(nll_tmp.alloc((size_t)n * gt * 8));
         nll_out = nll_tmp.as<double>();
     }
-    const bool t64 = nll_uses_n64r(n1, k);
-    const size_t dstride = (t64 ? (size_t)TILE64_PER : (size_t)npad * npad) * k * P;
+    const bool t64 = nll_uses_regs(n1, k);
+    const size_t dstride = (t64 ? regs_table_doubles(npad) : (size_t)npad * npad) * k * P;
     // one launch over (sample set, candidate) when the warp-per-candidate kernel takes the size; else one grid call per set
     if (!nll_uses_flow(n1, k) && k <= 8 && npad <= 144 && dstride * n * 8 <= ((size_t)1 << 30)) {
         DevBuf dtab(st), egrid(st);
         SM_TRY(dtab.alloc(dstride * n * 8));
-        SM_TRY(launch_dtab(xm.as<double>(), n1, k, t64 ? 0 : npad, p_axis, P, dtab.as<double>(), st, n));
+        SM_TRY(launch_dtab(xm.as<double>(), n1, k, t64 ? -npad : npad, p_axis, P, dtab.as<double>(), st, n));
         L.n += 1;
         NllArgs a{};
         a.X = xm.as<double>(); a.y = ym.as<double>(); a.n = n1; a.k = k; a.npad = npad;
@@ -208,7 +208,7 @@ int sm_krig_loo_grid(const double* X, const double* y, int n, int k, const doubl
         const size_t estride = dstride * T;
         if (npad <= 96 && k <= 4 && estride * n * 8 <= ((size_t)256 << 20)) {
             SM_TRY(egrid.alloc(estride * n * 8));
-            SM_TRY(launch_egrid(dtab.as<double>(), theta_axis, k * n, P, T, t64 ? 0 : npad, egrid.as<double>(), st));
+            SM_TRY(launch_egrid(dtab.as<double>(), theta_axis, k * n, P, T, t64 ? -npad : npad, egrid.as<double>(), st));
             L.n += 1;
             a.egrid = egrid.as<double>();
             a.egrid_model_stride = estride;
@@ -234,10 +234,10 @@ int sm_krig_nll_batch(const double* X, const double* y, int n, int k, const doub
     const int npad = sm_krig_npad(n);
     DevBuf lg(st), nll_tmp(st);
     const bool flow = nll_uses_flow(n, k);  // base-2, tile-packed table for the dataflow kernel
-    const bool t64 = nll_uses_n64r(n, k);
-    SM_TRY(lg.alloc((flow ? flow_table_doubles(n) : (t64 ? (size_t)TILE64_PER : (size_t)npad * npad)) * k * 8));
+    const bool t64 = nll_uses_regs(n, k);
+    SM_TRY(lg.alloc((flow ? flow_table_doubles(n) : (t64 ? regs_table_doubles(npad) : (size_t)npad * npad)) * k * 8));
     if (flow) SM_TRY(launch_log2tab(X, n, k, npad, lg.as<double>(), st));
-    else SM_TRY(launch_logtab(X, n, k, t64 ? 0 : npad, lg.as<double>(), st));
+    else SM_TRY(launch_logtab(X, n, k, t64 ? -npad : npad, lg.as<double>(), st));
     L.n += 1;
     if (!nll_out) {
         SM_TRY(nll_tmp.alloc((size_t)C * 8));

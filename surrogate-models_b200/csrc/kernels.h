@@ -18,7 +18,7 @@ struct NllArgs {
     const double* theta_axis;
     int T, P;
     const double* p_axis;  // [P] (grid mode; read by the extended-precision rescue pass only)
-    int tab_layout;      // 0: row-major [npad][npad] tables; 1: tile-packed (dataflow kernel); 2: tile64 (register-resident npad = 64 kernel)
+    int tab_layout;      // 0: row-major [npad][npad] tables; 1: tile-packed (dataflow kernel); 2: packed lower-triangle fragments (register-resident kernels, regs_table_doubles)
     const double* dtab;  // [k][P][npad][npad]
     const double* egrid;  // optional [k][P][T][npad][npad]: exp(-theta_axis[t] * dtab) -- product-form entries
     // list mode (MODE 1)
@@ -63,11 +63,18 @@ size_t nll_smem_bytes(int npad, int slots, int nwarps, size_t tile_bytes);
 cudaError_t launch_nll(NllArgs a, int mode, cudaStream_t st, long long* launches);
 cudaError_t launch_nll_small(const NllArgs& a, int mode, cudaStream_t st);
 cudaError_t launch_nll_n64(const NllArgs& a, int mode, cudaStream_t st);
-cudaError_t launch_nll_n64r(const NllArgs& a, int mode, cudaStream_t st);
-// true when the register-resident npad = 64 kernel takes (n, k): its tables use the tile64 layout (TILE64_PER doubles per
-// table instead of npad^2; launch_dtab / launch_logtab / launch_egrid build it when called with npad = 0)
-bool nll_uses_n64r(int n, int k);
-constexpr int TILE64_PER = 36 * 64;
+// register-resident warp-per-candidate kernels (krig_nll_regs.cu, one translation unit per NT = npad / 8)
+cudaError_t launch_nll_regs_5(const NllArgs& a, int mode, cudaStream_t st);
+cudaError_t launch_nll_regs_6(const NllArgs& a, int mode, cudaStream_t st);
+cudaError_t launch_nll_regs_7(const NllArgs& a, int mode, cudaStream_t st);
+cudaError_t launch_nll_regs_8(const NllArgs& a, int mode, cudaStream_t st);
+cudaError_t launch_nll_regs_9(const NllArgs& a, int mode, cudaStream_t st);
+cudaError_t launch_nll_regs_10(const NllArgs& a, int mode, cudaStream_t st);
+// true when one of them takes (n, k) (33 <= n <= 80, k <= 4).  Their tables use the packed lower-triangle layout: NT (NT + 1) / 2
+// tiles of 64 doubles, lane (r, q) owning entries (8I + r, 8J + q) and (8I + r, 8J + q + 4) at doubles [2l, 2l + 1] of tile (I, J);
+// launch_dtab / launch_logtab / launch_egrid build it when called with npad NEGATED.
+bool nll_uses_regs(int n, int k);
+__host__ __device__ inline size_t regs_table_doubles(int npad) { return (size_t)(npad / 8) * (npad / 8 + 1) / 2 * 64; }
 cudaError_t launch_nll_large(NllArgs a, int mode, cudaStream_t st);
 cudaError_t launch_nll_flow(NllArgs a, int mode, cudaStream_t st);
 bool nll_uses_flow(int n, int k);

@@ -23,7 +23,7 @@
 namespace smb {
 
 // ------------------------------------------------------------------------------------ tables
-// tile64 layout of a 64 x 64 lower-triangular table (the register-resident npad = 64 kernel): 36 tiles (I >= J) of 64 doubles,
+// packed fragment layout of a lower-triangular table (the register-resident kernels): NT (NT + 1) / 2 tiles (I >= J) of 64 doubles,
 // tile (I, J) at (I (I + 1) / 2 + J) * 64; inside a tile lane l = (r, q) owns doubles [2l, 2l + 1] = entries (8I + r, 8J + q) and
 // (8I + r, 8J + q + 4) -- one coalesced 512-byte request per tile and dimension, already in A-operand fragment element order
 __host__ __device__ __forceinline__ void tile64_ij(int e, int& i, int& j) {
@@ -37,12 +37,13 @@ __host__ __device__ __forceinline__ void tile64_ij(int e, int& i, int& j) {
 
 __global__ void dtab_kernel(const double* __restrict__ X, int n, int k, int npad,
                             const double* __restrict__ p_axis, int P, double* __restrict__ D) {
-    const size_t per = (size_t)npad * npad;
+    const size_t per = npad > 0 ? (size_t)npad * npad : 0;
     const size_t total = per * k * P;
     X += (size_t)blockIdx.y * n * k;  // blockIdx.y: sample set of a leave-one-out batch (0 for the plain call)
     D += (size_t)blockIdx.y * total;
-    if (npad == 0) {  // tile64 layout (krig_nll_n64r.cu): see tile64_ij
-        const size_t tot64 = (size_t)TILE64_PER * k * P;
+    if (npad < 0) {  // packed fragment layout of the register-resident kernels (krig_nll_regs.cu): see tile64_ij
+        const size_t TILE64_PER = regs_table_doubles(-npad);
+        const size_t tot64 = TILE64_PER * k * P;
         D += (size_t)blockIdx.y * tot64 - (size_t)blockIdx.y * total;
         for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot64; t += (size_t)gridDim.x * blockDim.x) {
             int i, j;
@@ -84,8 +85,9 @@ __global__ void egrid_kernel(const double* __restrict__ D, const double* __restr
 }
 
 __global__ void logtab_kernel(const double* __restrict__ X, int n, int k, int npad, double* __restrict__ LG) {
-    if (npad == 0) {  // tile64 layout
-        const size_t tot64 = (size_t)TILE64_PER * k;
+    if (npad < 0) {  // packed fragment layout
+        const size_t TILE64_PER = regs_table_doubles(-npad);
+        const size_t tot64 = TILE64_PER * k;
         for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot64; t += (size_t)gridDim.x * blockDim.x) {
             int i, j;
             tile64_ij((int)(t % TILE64_PER), i, j);
@@ -413,7 +415,7 @@ static cudaError_t launch_nll_fp64(NllArgs a, int mode, cudaStream_t st, long lo
 
 cudaError_t launch_dtab(const double* X, int n, int k, int npad, const double* p_axis, int P, double* D, cudaStream_t st,
                         int models) {
-    const size_t total = (npad ? (size_t)npad * npad : (size_t)TILE64_PER) * k * P;  // npad == 0: tile64 layout
+    const size_t total = (npad > 0 ? (size_t)npad * npad : regs_table_doubles(-npad)) * k * P;  // npad < 0: packed fragment layout
     int grid = (int)((total + 255) / 256);
     if (grid > 148 * 16) grid = 148 * 16;
     dtab_kernel<<<dim3(grid, models), 256, 0, st>>>(X, n, k, npad, p_axis, P, D);
@@ -457,14 +459,14 @@ cudaError_t launch_argmin_segments(const double* v, long long seg, int nseg, dou
     return cudaGetLastError();
 }
 cudaError_t launch_egrid(const double* dtab, const double* theta_axis, int k, int P, int T, int npad, double* E, cudaStream_t st) {
-    const size_t per = npad ? (size_t)npad * npad : (size_t)TILE64_PER, ntab = (size_t)k * P;
+    const size_t per = npad > 0 ? (size_t)npad * npad : regs_table_doubles(-npad), ntab = (size_t)k * P;
     size_t blocks = (ntab * T * per + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
     egrid_kernel<<<(int)blocks, 256, 0, st>>>(dtab, theta_axis, T, per, ntab, E);
     return cudaGetLastError();
 }
 cudaError_t launch_logtab(const double* X, int n, int k, int npad, double* LG, cudaStream_t st) {
-    const size_t total = (npad ? (size_t)npad * npad : (size_t)TILE64_PER) * k;
+    const size_t total = (npad > 0 ? (size_t)npad * npad : regs_table_doubles(-npad)) * k;
     int grid = (int)((total + 255) / 256);
     if (grid > 148 * 16) grid = 148 * 16;
     logtab_kernel<<<grid, 256, 0, st>>>(X, n, k, npad, LG);

@@ -1,4 +1,5 @@
-// Warp-per-candidate likelihood kernel for npad = 64 with the FACTOR RESIDENT IN REGISTERS.
+// Warp-per-candidate likelihood kernel with the FACTOR RESIDENT IN REGISTERS, npad = 8 NT for NT = 5 .. 10 (33 <= n <= 80;
+// NT = 8 is BASELINE config 2).  One translation unit per NT: build.py compiles this file with -DSMB_REGS_NT=<NT>.
 //
 // ncu on the shared-memory version (krig_nll_n64.cu, profiles/r02_n64_ncu.md): 2 070 shared-memory wavefronts + ~750
 // global / local ones per candidate keep the LSU data pipe 82 % busy -- every DMMA operand is an LDS.128 (4 wavefronts),
@@ -34,7 +35,11 @@ __device__ __forceinline__ void sfor(F&& f) {
     sfor_impl(f, std::make_integer_sequence<int, N>{});
 }
 
-constexpr int N64R_WARP_DOUBLES = 8 * 16 + 128;  // rhs rows | W tile | diagonal working tile
+#ifndef SMB_REGS_NT
+#define SMB_REGS_NT 8
+#endif
+constexpr int RNT = SMB_REGS_NT;                     // tile rows of the matrix
+constexpr int REGS_WARP_DOUBLES = RNT * 16 + 128;    // rhs rows | W tile | diagonal working tile
 
 // diag_factor (nll_small_common.cuh) with a filler: step j calls fill(integral_constant<j>) right after the reciprocal seed
 // of its pivot has been issued.  The filler issues independent DMMAs of the NEXT block column (its update over the block
@@ -91,30 +96,23 @@ __device__ __forceinline__ bool diag_factor_fill_r(double c0, double c1, double*
     return ok;
 }
 
-// one shared copy of the 8-step diagonal factor (no filler): used with -DN64R_SHARED_DIAG to measure what the 8 inlined,
-// filler-carrying copies cost in instruction-cache traffic
-__device__ __noinline__ bool diag_factor_shared(double c0, double c1, double* ts, double* wt, double& tp, int lane, double tau) {
-    return diag_factor(c0, c1, ts, wt, tp, lane, tau);
-}
+// 4 warps per CTA; 3 CTAs per SM at 168 registers up to NT = 8 (8 warps x 254 registers: -1 %, 16 x 128 with spills: +4 %,
+// measured at NT = 8), 2 CTAs at 254 registers above (up to 25 live tiles + 10 accumulator pairs)
+constexpr int REGS_WARPS = 4, REGS_MINB = (RNT <= 8) ? 3 : 2;
 
-#ifndef N64R_WARPS
-#define N64R_WARPS 4   // warps per CTA
-#define N64R_MINB 3    // CTAs per SM: 12 warps, 168 registers per thread (8 warps x 254 registers: -1 %, 16 x 128 with spills: +4 %)
-#endif
-
-template <int KD, int MODE, int WARPS, int MINB>
-__global__ void __launch_bounds__(32 * WARPS, MINB) krig_nll_n64r_kernel(const NllArgs a) {
+template <int NT, int KD, int MODE, int WARPS, int MINB>
+__global__ void __launch_bounds__(32 * WARPS, MINB) krig_nll_regs_kernel(const NllArgs a) {
     extern __shared__ __align__(16) double smem[];
-    constexpr int NPAD = 64;
+    constexpr int NPAD = 8 * NT;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int r = lane >> 2, q = lane & 3;
     double* etab = smem;           // [32]
-    double* y_s = etab + EXP_TAB;  // [64]
-    double* rhs_s = y_s + 64 + (size_t)wid * N64R_WARP_DOUBLES;  // [J][2][8]: rows y^T / 1^T
-    double* wscr = rhs_s + 8 * 16;                               // [64] W_J in operand order
+    double* y_s = etab + EXP_TAB;  // [NPAD]
+    double* rhs_s = y_s + NPAD + (size_t)wid * REGS_WARP_DOUBLES;  // [J][2][8]: rows y^T / 1^T
+    double* wscr = rhs_s + NT * 16;                              // [64] W_J in operand order
     double* dscr = wscr + 64;                                    // [64] diagonal tile, column-major working copy
     exp_table_init(etab, threadIdx.x, blockDim.x);
-    for (int j = threadIdx.x; j < 64; j += blockDim.x) y_s[j] = (j < a.n) ? a.y[j] : 0.0;
+    for (int j = threadIdx.x; j < NPAD; j += blockDim.x) y_s[j] = (j < a.n) ? a.y[j] : 0.0;
     __syncthreads();
 
     // sigma = [0,4,1,5,2,6,3,7]: row r of the permuted B operand is row sigma(r) of the tile
@@ -126,7 +124,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) krig_nll_n64r_kernel(const N
     const bool slot1 = (q >> 1) != 0;
     const int toff_off = 2 * lane;                       // this lane's pair inside a tile64 table tile
     const int toff_diag = 2 * src_sigma;                 // ... the pair of (row sigma(r), column q): the diagonal tile
-    constexpr long long per = TILE64_PER;
+    constexpr long long per = NT * (NT + 1) / 2 * 64;  // doubles of one packed table (regs_table_doubles)
     const long long first = (long long)blockIdx.x * nwarps + wid, stride = (long long)gridDim.x * nwarps;
     unsigned tk32 = 1;
     bool fast_decode = (MODE != 1);
@@ -200,13 +198,13 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) krig_nll_n64r_kernel(const N
         const double* ym = (a.models > 1) ? a.y + model * a.y_stride : nullptr;
         double prod = 1.0;
         bool ok = true;
-        double2 L[8][8];     // L[I][K], K < I: tile (I, K) as an A-operand fragment (.x = [r][q], .y = [r][q + 4]); registers
-        double acc[8][2];    // acc[g]: column being assembled, tile J + g, already in operand-fragment element order
+        double2 L[NT][NT];     // L[I][K], K < I: tile (I, K) as an A-operand fragment (.x = [r][q], .y = [r][q + 4]); registers
+        double acc[NT][2];    // acc[g]: column being assembled, tile J + g, already in operand-fragment element order
         double accr[2];      // its right-hand-side rows (lanes r < 2)
 #pragma unroll
-        for (int g = 0; g < 8; ++g) acc[g][0] = acc[g][1] = 0.0;
+        for (int g = 0; g < NT; ++g) acc[g][0] = acc[g][1] = 0.0;
         accr[0] = accr[1] = 0.0;
-        double2 tabv[8][KD];  // table values of the column being assembled: (column q, column q + 4) per tile and dimension
+        double2 tabv[NT][KD];  // table values of the column being assembled: (column q, column q + 4) per tile and dimension
 
         // table loads of tiles [G0, G1) of block column JJ
         auto load_tab = [&](auto JJc, auto G0c, auto G1c) {
@@ -239,13 +237,13 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) krig_nll_n64r_kernel(const N
             sfor<G1 - G0>([&](auto Gg) {
                 constexpr int g = G0 + decltype(Gg)::value;
                 if constexpr (g == 0) dmma(acc[0][0], acc[0][1], b.x, b.x);
-                else dmma(acc[g][0], acc[g][1], L[(JJ + g < 8 ? JJ + g : 7)][K].x, b.x);
+                else dmma(acc[g][0], acc[g][1], L[(JJ + g < NT ? JJ + g : NT - 1)][K].x, b.x);
             });
             if constexpr (RHS) dmma(accr[0], accr[1], a0, b.x);
             sfor<G1 - G0>([&](auto Gg) {
                 constexpr int g = G0 + decltype(Gg)::value;
                 if constexpr (g == 0) dmma(acc[0][0], acc[0][1], b.y, b.y);
-                else dmma(acc[g][0], acc[g][1], L[(JJ + g < 8 ? JJ + g : 7)][K].y, b.y);
+                else dmma(acc[g][0], acc[g][1], L[(JJ + g < NT ? JJ + g : NT - 1)][K].y, b.y);
             });
             if constexpr (RHS) dmma(accr[0], accr[1], a1, b.y);
         };
@@ -253,10 +251,10 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) krig_nll_n64r_kernel(const N
         using TrueT = std::integral_constant<bool, true>;
         using FalseT = std::integral_constant<bool, false>;
 
-        load_tab(I0{}, I0{}, std::integral_constant<int, 4>{});
-        sfor<8>([&](auto Jc) {
+        load_tab(I0{}, I0{}, std::integral_constant<int, (NT < 4 ? NT : 4)>{});
+        sfor<NT>([&](auto Jc) {
             constexpr int J = decltype(Jc)::value;
-            constexpr int cnt = 8 - J;  // tiles of this block column: I = J + g, g < cnt (g = 0: the diagonal tile)
+            constexpr int cnt = NT - J;  // tiles of this block column: I = J + g, g < cnt (g = 0: the diagonal tile)
             constexpr int c0n = cnt < 4 ? cnt : 4;
             // ------------------------------------------------------------ U: last k-step (K = J - 1), then the entries
             if constexpr (cnt > 4) load_tab(Jc, std::integral_constant<int, 4>{}, std::integral_constant<int, cnt>{});
@@ -293,48 +291,42 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) krig_nll_n64r_kernel(const N
                 dc1 = slot1 ? by : bx;
             }
             // the panel's C_IJ fragments wait in cfr[] for the inverse; acc[] is recycled for column J + 1
-            double2 cfr[8];
+            double2 cfr[NT];
             sfor<cnt>([&](auto Gg) {
                 constexpr int g = decltype(Gg)::value;
                 cfr[g] = make_double2(acc[g][0], acc[g][1]);
             });
 #pragma unroll
-            for (int g = 0; g < 8; ++g) acc[g][0] = acc[g][1] = 0.0;
+            for (int g = 0; g < NT; ++g) acc[g][0] = acc[g][1] = 0.0;
             accr[0] = accr[1] = 0.0;
             // ------------------------------------------------------------ D: diagonal tile; filler = column J + 1 over K < J
             double tp;
             constexpr int ncnt = cnt - 1;                       // tiles of column J + 1 (its diagonal tile included)
-            constexpr int ksteps = (J < 7) ? J : 0;             // k-steps K = 0 .. J-1 are available now
+            constexpr int ksteps = (J < NT - 1) ? J : 0;        // k-steps K = 0 .. J-1 are available now
             constexpr bool halves = (2 * ksteps <= 8) && ncnt >= 2;
             constexpr int hsplit = (ncnt + 1) / 2;
-            using JN = std::integral_constant<int, (J < 7 ? J + 1 : 7)>;
-#ifdef N64R_SHARED_DIAG
-            if constexpr (ksteps > 0) {
-                sfor<ksteps>([&](auto Kc) {
-                    constexpr int K = decltype(Kc)::value;
-                    kstep(JN{}, std::integral_constant<int, (K < 7 ? K : 0)>{}, I0{}, std::integral_constant<int, (ncnt > 0 ? ncnt : 1)>{}, TrueT{});
-                });
-            }
-            (void)halves; (void)hsplit;
-            ok = diag_factor_shared(dc0, dc1, dscr, wscr, tp, lane, tau) && ok;
-#else
+            using JN = std::integral_constant<int, (J < NT - 1 ? J + 1 : NT - 1)>;
             ok = diag_factor_fill_r(dc0, dc1, dscr, wscr, tp, lane, tau, [&](auto Sc) {
                 constexpr int s = decltype(Sc)::value;
                 if constexpr (halves) {   // two pivot steps per k-step: tiles [0, hsplit) | [hsplit, ncnt) + rhs
                     constexpr int K = s / 2;
                     if constexpr (K < ksteps) {
-                        using KC = std::integral_constant<int, (K < 7 ? K : 0)>;
+                        using KC = std::integral_constant<int, (K < NT - 1 ? K : 0)>;
                         if constexpr ((s & 1) == 0) kstep(JN{}, KC{}, I0{}, std::integral_constant<int, hsplit>{}, FalseT{});
                         else kstep(JN{}, KC{}, std::integral_constant<int, hsplit>{}, std::integral_constant<int, ncnt>{}, TrueT{});
                     }
-                } else if constexpr (s < ksteps) {
-                    kstep(JN{}, std::integral_constant<int, (s < 7 ? s : 0)>{}, I0{}, std::integral_constant<int, (ncnt > 0 ? ncnt : 1)>{}, TrueT{});
+                } else {                  // whole k-steps, ceil(ksteps / 8) per pivot step
+                    constexpr int per_step = (ksteps + 7) / 8;
+                    sfor<per_step>([&](auto Tc) {
+                        constexpr int K = s * per_step + decltype(Tc)::value;
+                        if constexpr (K < ksteps)
+                            kstep(JN{}, std::integral_constant<int, (K < NT - 1 ? K : 0)>{}, I0{}, std::integral_constant<int, (ncnt > 0 ? ncnt : 1)>{}, TrueT{});
+                    });
                 }
             }) && ok;
-#endif
             if (lane == J) prod = tp;
             // ------------------------------------------------------------ T: L_IJ = C_IJ W^T, W's rows permuted -> operand fragments
-            if constexpr (J < 7) load_tab(JN{}, I0{}, std::integral_constant<int, (ncnt < 4 ? ncnt : 4)>{});
+            if constexpr (J < NT - 1) load_tab(JN{}, I0{}, std::integral_constant<int, (ncnt < 4 ? ncnt : 4)>{});
             const double2 wf = *reinterpret_cast<const double2*>(wscr + ld_w_sigma);
             sfor<cnt>([&](auto Gg) {
                 constexpr int g = decltype(Gg)::value;
@@ -342,7 +334,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) krig_nll_n64r_kernel(const N
                     double t0 = 0.0, t1 = 0.0;
                     dmma(t0, t1, cfr[g].x, wf.x);
                     dmma(t0, t1, cfr[g].y, wf.y);
-                    L[(J + g < 8 ? J + g : 7)][J] = make_double2(t0, t1);
+                    L[(J + g < NT ? J + g : NT - 1)][J] = make_double2(t0, t1);
                 }
             });
             {
@@ -359,7 +351,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) krig_nll_n64r_kernel(const N
         // ---------------------------------------------------------------- epilogue (as krig_nll_small.cu)
         double nll = INFINITY;
         if (ok) {
-            const double logdet_half = 0.5 * warp_sum((lane < 8) ? log(prod) : 0.0);
+            const double logdet_half = 0.5 * warp_sum((lane < NT) ? log(prod) : 0.0);
             double sab = 0.0, sbb = 0.0;
             for (int j = lane; j < a.n; j += 32) {
                 const double av = rhs_s[(j >> 3) * 16 + (j & 7)], bv = rhs_s[(j >> 3) * 16 + 8 + (j & 7)];
@@ -383,32 +375,34 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) krig_nll_n64r_kernel(const N
 }
 
 
-template <int KD, int MODE, int WARPS, int MINB>
-static cudaError_t launch_n64r_t(const NllArgs& a, cudaStream_t st) {
-    const size_t smem = (EXP_TAB + 64) * 8 + (size_t)WARPS * N64R_WARP_DOUBLES * 8;
-    long long grid = (long long)sm_count() * MINB;
-    const long long need = (a.C + WARPS - 1) / WARPS;
+template <int KD, int MODE>
+static cudaError_t launch_regs_t(const NllArgs& a, cudaStream_t st) {
+    const size_t smem = (EXP_TAB + 8 * RNT) * 8 + (size_t)REGS_WARPS * REGS_WARP_DOUBLES * 8;
+    long long grid = (long long)sm_count() * REGS_MINB;
+    const long long need = (a.C + REGS_WARPS - 1) / REGS_WARPS;
     if (grid > need) grid = need;
-    krig_nll_n64r_kernel<KD, MODE, WARPS, MINB><<<(int)grid, 32 * WARPS, smem, st>>>(a);
+    krig_nll_regs_kernel<RNT, KD, MODE, REGS_WARPS, REGS_MINB><<<(int)grid, 32 * REGS_WARPS, smem, st>>>(a);
     return cudaGetLastError();
 }
 
-// npad == 64 and k <= 4, otherwise cudaErrorNotSupported (the caller falls back to the shared-memory kernels)
-cudaError_t launch_nll_n64r(const NllArgs& a, int mode, cudaStream_t st) {
-    if (a.npad != 64 || a.k < 1 || a.k > 4 || a.C <= 0) return cudaErrorNotSupported;
+// npad == 8 NT of this translation unit and k <= 4, otherwise cudaErrorNotSupported
+#define SMB_CAT2(a, b) a##b
+#define SMB_CAT(a, b) SMB_CAT2(a, b)
+cudaError_t SMB_CAT(launch_nll_regs_, SMB_REGS_NT)(const NllArgs& a, int mode, cudaStream_t st) {
+    if (a.npad != 8 * RNT || a.k < 1 || a.k > 4 || a.C <= 0) return cudaErrorNotSupported;
     const int m = (mode == 0 && a.egrid) ? 2 : mode;
-#define SMB_N64R(KD)                                                     \
-    case KD:                                                             \
-        if (m == 2) return launch_n64r_t<KD, 2, N64R_WARPS, N64R_MINB>(a, st); \
-        if (m == 0) return launch_n64r_t<KD, 0, N64R_WARPS, N64R_MINB>(a, st); \
-        return launch_n64r_t<KD, 1, N64R_WARPS, N64R_MINB>(a, st);
+#define SMB_REGS(KD)                                     \
+    case KD:                                             \
+        if (m == 2) return launch_regs_t<KD, 2>(a, st);  \
+        if (m == 0) return launch_regs_t<KD, 0>(a, st);  \
+        return launch_regs_t<KD, 1>(a, st);
     switch (a.k) {
-        SMB_N64R(1)
-        SMB_N64R(2)
-        SMB_N64R(3)
-        SMB_N64R(4)
+        SMB_REGS(1)
+        SMB_REGS(2)
+        SMB_REGS(3)
+        SMB_REGS(4)
     }
-#undef SMB_N64R
+#undef SMB_REGS
     return cudaErrorNotSupported;
 }
 

@@ -409,12 +409,13 @@ static cudaError_t launch_small_k(const NllArgs& a, int mode, cudaStream_t st) {
 
 // n <= 144 and k <= 8: the specialised kernel; anything else returns cudaErrorNotSupported and the caller
 // uses the generic engine
-bool nll_uses_n64r(int n, int k) {
+bool nll_uses_regs(int n, int k) {
     static const bool off = [] {
         const char *v = getenv("SMB_N64_OFF"), *w = getenv("SMB_N64_VARIANT"), *g = getenv("SMB_FORCE_GENERIC");
         return (v && v[0] == '1') || (w && w[0] == 's') || (g && g[0] == '1');
     }();
-    return !off && n > 56 && n <= 64 && k >= 1 && k <= 4 && !nll_uses_flow(n, k);
+    const int NT = (n + 7) / 8;
+    return !off && NT >= 5 && NT <= 10 && k >= 1 && k <= 4 && !nll_uses_flow(n, k);
 }
 
 cudaError_t launch_nll_small(const NllArgs& a, int mode, cudaStream_t st) {
@@ -423,7 +424,17 @@ cudaError_t launch_nll_small(const NllArgs& a, int mode, cudaStream_t st) {
     // npad = 64, k <= 4: the statically unrolled kernel (krig_nll_n64.cu; SMB_N64_OFF=1 keeps the generic one, used by the
     // cross-check in the tests -- the two are bit-identical)
     static const bool n64_off = [] { const char* v = getenv("SMB_N64_OFF"); return v && v[0] == '1'; }();
-    if (a.tab_layout == 2) return launch_nll_n64r(a, mode, st);  // factor in registers: the caller built tile64 tables for it
+    if (a.tab_layout == 2) {  // factor in registers: the caller built packed-fragment tables for it (nll_uses_regs)
+        switch (NT) {
+            case 5: return launch_nll_regs_5(a, mode, st);
+            case 6: return launch_nll_regs_6(a, mode, st);
+            case 7: return launch_nll_regs_7(a, mode, st);
+            case 8: return launch_nll_regs_8(a, mode, st);
+            case 9: return launch_nll_regs_9(a, mode, st);
+            case 10: return launch_nll_regs_10(a, mode, st);
+            default: return cudaErrorInvalidValue;
+        }
+    }
     if (!n64_off && a.npad == 64 && a.k <= 4) {                  // factor in shared memory, statically unrolled (SMB_N64_VARIANT=s)
         const cudaError_t e = launch_nll_n64(a, mode, st);
         if (e != cudaErrorNotSupported) return e;

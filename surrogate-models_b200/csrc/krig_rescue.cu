@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(THREADS) krig_rescue_kernel(const NllArgs a, c
     size_t* toff = reinterpret_cast<size_t*>(pw + KMAX);  // [KMAX] offset of table (d, q_d) in a.dtab
     dd* A = ws_stride ? gws + (size_t)blockIdx.x * ws_stride : reinterpret_cast<dd*>(toff + KMAX);
     const bool tabbed = (mode == 0) && a.dtab != nullptr && tab_rowmajor;  // layout 0 (row-major) or 2 (tile64)
-    const size_t tper = (a.tab_layout == 2) ? (size_t)TILE64_PER : (size_t)a.npad * a.npad;
+    const size_t tper = (a.tab_layout == 2) ? regs_table_doubles(a.npad) : (size_t)a.npad * a.npad;
     const int n = a.n, k = a.k, m = n + 2;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned long long total = *cnt;

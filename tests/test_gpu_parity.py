@@ -1241,3 +1241,66 @@ def test_device_exp10_matches_scalar_pow_and_pool_trim(K):
     assert np.max(np.abs(got - want) / want) < 3e-16
     assert int((np.power(10., e) != want).sum()) > 10 * max(mism, 1)
     assert _cabi.lib().sm_b200_trim_pool() == 0
+
+
+# ------------------------------------------------------------------------------------------ full BASELINE sizes: size-independent properties
+def test_c3_full_1e5_candidates_properties(gold, K):
+    """BASELINE config 3 at full size (n = 1024, k = 8, 10^5 list-mode candidates, ~2 s): the reference needs 107 h for this,
+    so beyond the 10 reference-evaluated rows the check is by properties the likelihood has for any implementation --
+    independence of the batch a candidate sits in (bit for bit), invariance under a permutation of the samples, first-minimum
+    semantics of the reduction."""
+    g = gold('c3_lhs1024')
+    X, y = workloads.c3_lhs1024()
+    e, p = workloads.c3_candidates(100000, 8)
+    k = K(X, y)
+    nll, bv, bi = k.likelihood_batch(e, p, return_best=True)
+    assert nll.shape == (100000,) and np.all(np.isfinite(nll))
+    assert check_values(nll[g['sel']], g['nll'], g['cond']) == len(g['sel'])           # rows the reference evaluated
+    assert bi == orc.first_min_vec(nll) and bv == nll[bi]
+    sub = np.r_[0:300, 49990:50010, 99900:100000]
+    assert np.array_equal(k.likelihood_batch(e[sub], p[sub]), nll[sub])                 # a candidate's value does not depend on its batch
+    perm = np.random.default_rng(1).permutation(1024)
+    kp = K(X[perm], y[perm])
+    some = np.arange(0, 100000, 1571)
+    assert np.max(rel(kp.likelihood_batch(e[some], p[some]), nll[some])) < 1e-9         # sample order is irrelevant
+
+
+def test_c5_full_1e8_queries_properties(gold, K):
+    """BASELINE config 5 at full size: 10^8 mesh queries (value + MSE) on the kriging_r3 model, generated on the device.
+    Checked: a random sample of 4 000 mesh points against the oracle and the reference fixture's model, MSE >= 0 and finite
+    everywhere, slices of the mesh reproduce the full run bit for bit (what the ranks compute), checksum of checksums."""
+    import torch
+    from sm_b200 import device
+    g = gold('c5_kriging_r3')
+    X, y = g['X'], g['y']
+    k = K(X, y)
+    th, p = [0.05, 0.05], [1.9, 1.9]
+    k.update_param(th, p)
+    M = 10000
+    yy = device.empty(M * M)
+    mm = device.empty(M * M)
+    step = 25_000_000
+    for lo in range(0, M * M, step):                                   # 4 slices: 400 MB of coordinates at a time
+        xq = device.mesh_points([-2., -2.], [12., 12.], [M, M], lo, step)
+        a, b = k.predict_device(xq, True)
+        yy[lo:lo + step], mm[lo:lo + step] = a, b
+        del xq, a, b
+    assert bool(torch.isfinite(yy).all()) and bool(torch.isfinite(mm).all()) and float(mm.min()) >= 0.0
+    idx = np.sort(np.random.default_rng(3).integers(0, M * M, 4000))
+    ax = np.linspace(-2., 12., M)
+    pts = np.stack([ax[idx // M], ax[idx % M]], axis=1)
+    yr, mr = orc.predict_chol(X, y, th, p, pts, True)
+    it = torch.from_numpy(idx).to(yy.device)
+    assert np.max(rel(yy[it].cpu().numpy(), yr)) < 1e-9
+    assert np.max(np.abs(mm[it].cpu().numpy() - mr)) < 1e-9 * k._fit['sigma2']
+    assert np.max(rel(yy[it].cpu().numpy(), orc.predict_lu(X, y, th, p, pts))) < 1e-9    # the reference's own formulation
+    # a different slicing (7 ragged slices) gives the same bits
+    acc = torch.zeros((), dtype=torch.float64, device=yy.device)
+    for r in range(7):
+        lo, hi = M * M * r // 7, M * M * (r + 1) // 7
+        xq = device.mesh_points([-2., -2.], [12., 12.], [M, M], lo, hi - lo)
+        a, _ = k.predict_device(xq, True)
+        assert bool(torch.equal(a, yy[lo:hi]))
+        acc += a.sum()
+        del xq, a
+    assert abs(float(acc) - float(yy.sum())) <= 1e-9 * abs(float(yy.sum()))
