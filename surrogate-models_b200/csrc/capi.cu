@@ -124,7 +124,7 @@ int sm_krig_nll_grid(const double* X, const double* y, int n, int k, const doubl
     const int npad = sm_krig_npad(n);
     DevBuf dtab(st), nll_tmp(st);
     const bool flow = nll_uses_flow(n, k);  // tile-packed lower-triangle tables for the dataflow kernel
-    const bool t64 = nll_uses_regs(n, k);   // packed-fragment tables for the register-resident kernels
+    const bool t64 = nll_uses_regs(n, k, 0);   // packed-fragment tables for the register-resident kernels
     const size_t tper = t64 ? regs_table_doubles(npad) : (size_t)npad * npad;
     if (flow) {
         SM_TRY(dtab.alloc(flow_table_doubles(n) * k * P * 8));
@@ -190,7 +190,7 @@ int sm_krig_loo_grid(const double* X, const double* y, int n, int k, const doubl
         SM_TRY(nll_tmp.alloc((size_t)n * gt * 8));
         nll_out = nll_tmp.as<double>();
     }
-    const bool t64 = nll_uses_regs(n1, k);
+    const bool t64 = nll_uses_regs(n1, k, 0);
     const size_t dstride = (t64 ? regs_table_doubles(npad) : (size_t)npad * npad) * k * P;
     // one launch over (sample set, candidate) when the warp-per-candidate kernel takes the size; else one grid call per set
     if (!nll_uses_flow(n1, k) && k <= 8 && npad <= 144 && dstride * n * 8 <= ((size_t)1 << 30)) {
@@ -234,7 +234,7 @@ int sm_krig_nll_batch(const double* X, const double* y, int n, int k, const doub
     const int npad = sm_krig_npad(n);
     DevBuf lg(st), nll_tmp(st);
     const bool flow = nll_uses_flow(n, k);  // base-2, tile-packed table for the dataflow kernel
-    const bool t64 = nll_uses_regs(n, k);
+    const bool t64 = nll_uses_regs(n, k, 1);
     SM_TRY(lg.alloc((flow ? flow_table_doubles(n) : (t64 ? regs_table_doubles(npad) : (size_t)npad * npad)) * k * 8));
     if (flow) SM_TRY(launch_log2tab(X, n, k, npad, lg.as<double>(), st));
     else SM_TRY(launch_logtab(X, n, k, t64 ? -npad : npad, lg.as<double>(), st));

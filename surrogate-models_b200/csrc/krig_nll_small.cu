@@ -409,12 +409,16 @@ static cudaError_t launch_small_k(const NllArgs& a, int mode, cudaStream_t st) {
 
 // n <= 144 and k <= 8: the specialised kernel; anything else returns cudaErrorNotSupported and the caller
 // uses the generic engine
-bool nll_uses_regs(int n, int k) {
+bool nll_uses_regs(int n, int k, int mode) {
     static const bool off = [] {
         const char *v = getenv("SMB_N64_OFF"), *w = getenv("SMB_N64_VARIANT"), *g = getenv("SMB_FORCE_GENERIC");
         return (v && v[0] == '1') || (w && w[0] == 's') || (g && g[0] == '1');
     }();
     const int NT = (n + 7) / 8;
+    // measured (profiles/r02_regs_kernel_sizes.txt): grid mode +10 .. +42 % over the shared-memory kernel for every NT = 5 .. 10,
+    // list mode +10 .. +15 % at k = 2; list mode with k = 4 at NT = 10 is 7 % slower (exp per entry and dimension on top of
+    // 25 live tiles), so list mode above NT = 8 keeps the shared-memory kernel for k >= 3
+    if (mode == 1 && NT > 8 && k >= 3) return false;
     return !off && NT >= 5 && NT <= 10 && k >= 1 && k <= 4 && !nll_uses_flow(n, k);
 }
 

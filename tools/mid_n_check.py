@@ -14,7 +14,7 @@ from sm_b200 import _cabi, device, workloads  # noqa: E402
 L = _cabi.lib()
 SIZES = [(128, 2, 20000), (136, 2, 20000), (144, 2, 20000), (144, 8, 20000), (152, 2, 20000)]
 if len(sys.argv) > 1:  # n,k[;n,k...]
-    SIZES = [(int(t.split(',')[0]), int(t.split(',')[1]), 20000) for t in sys.argv[1].split(';')]
+    SIZES = [(int(t.split(',')[0]), int(t.split(',')[1]), 200000 if int(t.split(",")[0]) <= 96 else 20000) for t in sys.argv[1].split(';')]
 for n, k, C in SIZES:
     X, y = workloads.c3_lhs1024(n=n, k=k)
     e, p = workloads.c3_candidates(C, k)
@@ -33,7 +33,7 @@ for n, k, C in SIZES:
     if k > 2:
         print(f'n={n:4d} k={k}: list {C / ms * 1e3:.4g} evals/s {fl * C / ms / 1e9:.2f} TFLOP/s', flush=True)
         continue
-    T, P = 10, 5
+    T, P = 20, 10
     bv, bi, _ = kr.likelihood_grid(T, P)
     torch.cuda.synchronize()
     a.record(); kr.likelihood_grid(T, P, return_nll=False); b.record(); torch.cuda.synchronize()
