@@ -316,7 +316,7 @@ def test_c3_n1024_k8(gold, K):
     assert np.max(rel(yy, yr)) < 1e-8 and np.max(np.abs(mse - mr)) < 1e-8 * k._fit['sigma2']
 
 
-@pytest.mark.parametrize('n,k_', [(1, 1), (2, 1), (7, 2), (13, 3), (30, 6), (64, 8), (65, 2), (73, 2), (80, 5), (100, 7), (90, 4), (96, 3), (97, 2), (104, 2), (128, 4), (129, 4), (144, 2),
+@pytest.mark.parametrize('n,k_', [(1, 1), (2, 1), (7, 2), (13, 3), (30, 6), (33, 1), (40, 4), (47, 3), (56, 2), (57, 4), (64, 8), (65, 2), (72, 3), (79, 1), (80, 4), (73, 2), (80, 5), (100, 7), (90, 4), (96, 3), (97, 2), (104, 2), (128, 4), (129, 4), (144, 2),
                                   (225, 3), (230, 16)])
 def test_ragged_sizes_against_oracle(K, n, k_):
     """sizes straddling every kernel variant / padding boundary (8-tiles; n <= 144 and k <= 8 warp-per-candidate,
@@ -1304,3 +1304,25 @@ def test_c5_full_1e8_queries_properties(gold, K):
         acc += a.sum()
         del xq, a
     assert abs(float(acc) - float(yy.sum())) <= 1e-9 * abs(float(yy.sum()))
+
+
+@pytest.mark.parametrize('n,k_,T,P', [(41, 1, 7, 4), (49, 3, 3, 2), (58, 2, 5, 3), (66, 4, 2, 2), (73, 2, 4, 3), (81, 3, 3, 2)])
+def test_register_resident_kernels_grid_mode_and_loo(K, n, k_, T, P):
+    """every tile count of the register-resident kernels (NT = 5 .. 10 for the full set and for the n - 1 leave-one-out sets),
+    grid mode with and without product tables, against the oracle's LU form and against the per-model calls"""
+    rng = np.random.default_rng(7 * n + k_)
+    X = rng.uniform(0, 10, (n, k_))
+    y = np.cos(X.sum(axis=1)) + 0.05 * X[:, 0] ** 2
+    k = K(X, y)
+    param, idx, nll = k.grid_search(T, P, return_nll=True)
+    e, q = orc.grid_candidates(k_, T, P)
+    sel = np.arange(0, e.shape[0], max(1, e.shape[0] // 60))
+    ref = np.array([orc.nll_opti_exp(X, y, np.concatenate([e[c], q[c]]), 'lu') for c in sel])
+    cond = np.array([orc.cond2(orc.corr_matrix(X, 10. ** e[c], q[c])) for c in sel])
+    check_values(nll[sel], ref, cond)
+    assert idx == orc.first_min_vec(nll)
+    guesses, lnll = k.loo_grid_guesses(T, P, return_nll=True)
+    for m in (0, n // 2, n - 1):
+        km = K(np.delete(X, m, axis=0), np.delete(y, m))
+        pm, im, rm = km.grid_search(T, P, return_nll=True)
+        assert np.array_equal(lnll[m], rm, equal_nan=True) and guesses[m] == (pm, im)
