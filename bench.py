@@ -330,10 +330,13 @@ def run_gpu(args):
     launches = _cabi.launch_count() - n0
     clocks = sampler.stop() if rank == 0 else None
     ms = float(np.sum([a.elapsed_time(b) for a, b in ev]))
+    per_rank_ms = [ms / args.steps]
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device='cuda')
-        td.all_reduce(t, op=td.ReduceOp.MAX)
-        ms = float(t.item())
+        allms = torch.empty(world, dtype=torch.float64, device='cuda')
+        td.all_gather_into_tensor(allms, t)
+        per_rank_ms = [float(v) / args.steps for v in allms.tolist()]
+        ms = float(allms.max().item())
     ms_per_step = ms / args.steps
     value = world * CAND_PER_GPU / (ms_per_step * 1e-3)
 
@@ -623,7 +626,7 @@ def run_gpu(args):
                                    f'= generate_grid(func,2,{T_SEC},{P}) flat range [r*1e6,(r+1)*1e6)',
                        'candidates_per_gpu': CAND_PER_GPU, 'l2': 'flushed (256 MiB write) between timed steps',
                        'parallelism': f'candidate-sharded x{world}; all_gather of (nll_min, index) only'},
-            'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline,
+            'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'per_rank_ms_per_step': per_rank_ms,
             'cpu_baseline': cpu, 'secondary': secondary, 'secondary_c3': secondary_c3, 'secondary_c4': secondary_c4,
             'result': parity,
         }

@@ -480,10 +480,13 @@ class Kriging:
             if mse is not None:
                 mse.fill_(float('nan'))
             return y, mse
+        want_mse = mse is not None and f.get('info', 0) != 3
         _cabi.check(L.sm_krig_predict(device.ptr(d['X']), self._n, self._k, device.ptr(f['theta']), device.ptr(f['p']),
-                                      device.ptr(f['w']), f['mu'], f['sigma2'], device.ptr(f['Mop']),
+                                      device.ptr(f['w']), f['mu'], f['sigma2'], device.ptr(f['Mop']) if want_mse else None,
                                       device.ptr(f['b']), device.ptr(f['rres']), device.ptr(xq_dev), nq,
-                                      device.ptr(y), device.ptr(mse), device.stream()))
+                                      device.ptr(y), device.ptr(mse) if want_mse else None, device.stream()))
+        if mse is not None and not want_mse:
+            mse.fill_(float('nan'))  # info 3: weights from the double-double factorisation, but no fp64 factor for L^-1
         return y, mse
 
     # ------------------------------------------------------------------ likelihood surface plots
