@@ -440,10 +440,18 @@ def run_gpu(args):
     xq = device.mesh_points([-2., -2.], [12., 12.], [m, m])
     pred_ms = timed_ms(lambda: k5.predict_device(xq, True))
     pred_mean_ms = timed_ms(lambda: k5.predict_device(xq, False))
+    # the same mesh through the mesh entry point (per-dimension correlation factors tabulated over the axes, no coordinates read)
+    mesh_ms = timed_ms(lambda: k5.predict_mesh([-2., -2.], [12., 12.], [m, m], as_device=True))
     f_mse = 2 * n5 * 2 + 2 * n5 + n5 * n5 + 3 * n5          # 2nk + 2n + n^2 + 3n flop per query with MSE
     t_pipe = nq5 * (f_mse / P_FMA + n5 / P_EXP + 2 * n5 / P_POW)   # + n exp + n k pow on the same fp64 pipe
+    f_mesh = n5 * n5 + 3 * n5 + n5                            # MSE contraction + reductions + one multiply per (query, sample)
     secondary = {'metric': 'kriging predictions/s (value+MSE, n=36, k=2, p=1.9)', 'value': world * nq5 / (pred_ms * 1e-3),
                  'unit': 'predictions/s', 'queries_per_gpu': nq5, 'ms': pred_ms,
+                 'value_note': 'arbitrary query points (sm_krig_predict); mesh_path = the same mesh through sm_krig_predict_mesh',
+                 'mesh_path': {'value': world * nq5 / (mesh_ms * 1e-3), 'unit': 'predictions/s', 'ms': mesh_ms,
+                               'kernel': 'krig_predict_mse_kernel<8,2,2,MESH>', 'flops_per_query': f_mesh,
+                               'frac': f_mesh * nq5 / (mesh_ms * 1e-3) / P_FMA,
+                               'hbm_gbs_achieved': nq5 * 16 / (mesh_ms * 1e-3) / 1e9},
                  'mean_only_predictions_per_s': world * nq5 / (pred_mean_ms * 1e-3),
                  'roofline': {'bound': 'tensor', 'bound_detail': 'fp64 pipe: n^2 DMMA contraction + n exp + n k pow per query; not HBM '
                                                                  '(32 B per query)', 'kernel': 'krig_predict_mse_kernel<8,2,2>',
@@ -476,8 +484,9 @@ def run_gpu(args):
     s_host = wall_max(e2e_host, 2)
     del xqh
     secondary['e2e'] = {'value': world * nq5 / s_mesh, 'unit': 'predictions/s', 'h2d_bytes_per_step': int(8 * (X5.size + y5.size + 4)),
-                        'd2h_bytes_per_step': int(16 * nq5), 'api': 'sm_krig_fit_predict_mesh_host (fit + on-device mesh + predict, '
-                        'results to pinned host memory, 3 streams)', 'ratio_to_device_rate': (nq5 / s_mesh) / (nq5 / (pred_ms * 1e-3)),
+                        'd2h_bytes_per_step': int(16 * nq5), 'api': 'sm_krig_fit_predict_mesh_host (fit + tabulated mesh prediction, '
+                        'results to pinned host memory, 3 streams)', 'ratio_to_device_rate': (nq5 / s_mesh) / (nq5 / (mesh_ms * 1e-3)),
+                        'd2h_gbs_achieved': 16 * nq5 / s_mesh / 1e9, 'note': 'bound by the device-to-host copy of the results (16 B per query)',
                         'host_queries': {'value': world * nq5 / s_host, 'h2d_bytes_per_step': int(16 * nq5), 'd2h_bytes_per_step': int(16 * nq5),
                                          'api': 'sm_krig_fit_predict_host (pinned host queries, chunked over 3 streams)'}}
     # strong scaling of north-star config 5: 1e8 queries IN TOTAL (10^4 x 10^4 mesh over [-2,12]^2) split over the ranks
@@ -485,13 +494,12 @@ def run_gpu(args):
     q_lo, q_hi = dist.shard_range(M5 * M5, rank, world)
 
     def c5_total():
-        xs = device.mesh_points([-2., -2.], [12., 12.], [M5, M5], q_lo, q_hi - q_lo)
-        k5.predict_device(xs, True)
+        k5.predict_mesh([-2., -2.], [12., 12.], [M5, M5], q_lo, q_hi - q_lo, as_device=True)
     c5_total()
     torch.cuda.synchronize()
     s_c5 = wall_max(c5_total, 2)
     secondary['strong_scaling_c5'] = {'queries_total': M5 * M5, 'n_gpus': world, 'seconds': s_c5, 'value': M5 * M5 / s_c5,
-                                      'unit': 'predictions/s', 'what': 'mesh generation + value+MSE prediction of this rank\'s '
+                                      'unit': 'predictions/s', 'what': 'Kriging.predict_mesh (value + MSE) on this rank\'s '
                                       'contiguous slice, results stay sharded on the devices; max over ranks'}
     # C3 shape: 8-D Kriging on LHS samples, explicit candidate list (list mode), n = 1024 plus two neighbours of the
     # large-n kernel range.  fractions: FMA-only (n^3/3 + (k+2) n^2 flop at the measured fp64 peak) and the

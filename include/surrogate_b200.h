@@ -129,7 +129,15 @@ int sm_krig_fit_predict_host(const double* X, const double* y, int n, int k, con
  * lo, hi, m are HOST arrays of k entries; out (device) receives count * k doubles. */
 int sm_mesh_points(const double* lo, const double* hi, const int64_t* m, int k, int64_t begin, int64_t count, double* out,
                    void* stream);
-/* sm_krig_fit_predict_host with the queries generated on the device by sm_mesh_points: only the results cross PCIe */
+/* sm_krig_predict at points [begin, begin + count) of such a mesh WITHOUT materialising them.  For k <= 4, n <= 128 and
+ * mse_out != NULL the per-dimension terms theta_d |x_d - x_id|^p_d are tabulated once per call over the mesh axes (sum_d m_d x n
+ * entries) as exp(-theta_d |dx|^p_d) factors, so every (query, sample) pair costs k - 1 multiplies instead of k powers and an exp
+ * -- within k ulp of sm_krig_predict on the points sm_mesh_points generates (the surface plots of the reference, examples/kriging_r3.py:59-70, and BASELINE config 5);
+ * other shapes generate the points on the device and call sm_krig_predict.  lo, hi, m: HOST arrays. */
+int sm_krig_predict_mesh(const double* X, int n, int k, const double* theta, const double* p, const double* w, double mu,
+                         double sigma2, const double* Mop, const double* b, const double* rres, const double* lo, const double* hi,
+                         const int64_t* m, int64_t begin, int64_t count, double* y_out, double* mse_out, void* stream);
+/* sm_krig_fit_predict_host on a mesh through sm_krig_predict_mesh: only the results cross PCIe */
 int sm_krig_fit_predict_mesh_host(const double* X, const double* y, int n, int k, const double* theta, const double* p,
                                   const double* lo, const double* hi, const int64_t* m, int64_t begin, int64_t count,
                                   double* y_out, double* mse_out, double* scalars);

@@ -296,6 +296,26 @@ int sm_krig_predict(const double* X, int n, int k, const double* theta, const do
     return (int)e;
 }
 
+int sm_krig_predict_mesh(const double* X, int n, int k, const double* theta, const double* p, const double* w, double mu,
+                         double sigma2, const double* Mop, const double* b, const double* rres, const double* lo, const double* hi,
+                         const int64_t* m, int64_t begin, int64_t count, double* y_out, double* mse_out, void* stream) {
+    if (!X || !theta || !p || !w || !lo || !hi || !m || !y_out || bad_nk(n, k) || begin < 0 || count < 0) return SM_E_BADARG;
+    if (mse_out && (!Mop || !b || !rres)) return SM_E_BADARG;
+    keep_pool_cached();
+    long long mm[SM_KMAX];
+    for (int d = 0; d < k; ++d) {
+        if (m[d] < 1) return SM_E_BADARG;
+        mm[d] = m[d];
+    }
+    Launches L;
+    PredictArgs a{};
+    a.X = X; a.n = n; a.k = k; a.npad = sm_krig_npad(n);
+    a.theta = theta; a.p = p; a.w = w; a.mu = mu; a.sigma2 = sigma2;
+    a.Mop = Mop; a.b = b; a.rres = rres; a.Xq = nullptr; a.Nq = count; a.y_out = y_out; a.mse_out = mse_out;
+    SM_TRY(launch_krig_predict_mesh(a, lo, hi, mm, begin, (cudaStream_t)stream, &L.n));
+    return 0;
+}
+
 int sm_rbf_fit(const double* X, const double* y, int n, int k, int kind, double a, double* coeff, int* info,
                void* stream) {
     if (!X || !y || !coeff || !info || bad_nk(n, k) || kind < 0 || kind > 4) return SM_E_BADARG;
@@ -429,15 +449,14 @@ int fit_predict_chunked(const double* X, const double* y, int n, int k, const do
         const int s = c % NS;
         const int64_t cnt = (Nq - done < chunk) ? Nq - done : chunk;
         cudaError_t e = cudaSuccess;
-        if (mesh) {
-            long long mm[SM_KMAX];
-            for (int d = 0; d < k; ++d) mm[d] = mesh->m[d];
-            e = launch_mesh_points(mesh->lo, mesh->hi, mm, k, mesh->begin + done, cnt, bq[s], ss[s], &L.n);
+        if (mesh) {  // tabulated mesh path (or on-device point generation inside it): no query coordinates cross PCIe
+            err = sm_krig_predict_mesh(dX, n, k, dth, dp, dw, sc[1], sc[2], dM, db, dr, mesh->lo, mesh->hi, mesh->m,
+                                       mesh->begin + done, cnt, by[s], mse_out ? bm[s] : nullptr, ss[s]);
         } else {
             e = cudaMemcpyAsync(bq[s], Xq + (size_t)done * k, (size_t)cnt * k * 8, cudaMemcpyHostToDevice, ss[s]);
+            if (e != cudaSuccess) { err = (int)e; break; }
+            err = sm_krig_predict(dX, n, k, dth, dp, dw, sc[1], sc[2], dM, db, dr, bq[s], cnt, by[s], mse_out ? bm[s] : nullptr, ss[s]);
         }
-        if (e != cudaSuccess) { err = (int)e; break; }
-        err = sm_krig_predict(dX, n, k, dth, dp, dw, sc[1], sc[2], dM, db, dr, bq[s], cnt, by[s], mse_out ? bm[s] : nullptr, ss[s]);
         if (err) break;
         e = cudaMemcpyAsync(y_out + done, by[s], (size_t)cnt * 8, cudaMemcpyDeviceToHost, ss[s]);
         if (e == cudaSuccess && mse_out) e = cudaMemcpyAsync(mse_out + done, bm[s], (size_t)cnt * 8, cudaMemcpyDeviceToHost, ss[s]);

@@ -127,8 +127,14 @@ struct PredictArgs {
     long long Nq;
     double* y_out;    // [Nq]
     double* mse_out;  // [Nq] or null
+    // mesh queries (sm_krig_predict_mesh): query q is point mesh_begin + q of the full-factorial mesh with mesh_m[d] points per
+    // dimension (last dimension fastest); mesh_tab[(mesh_off[d] + ix) * npad + i] = exp(-theta_d |axis_d[ix] - x_id| ^ p_d).  Xq unused.
+    const double* mesh_tab;
+    long long mesh_m[4], mesh_off[4], mesh_begin;
 };
 cudaError_t launch_krig_predict(const PredictArgs& a, cudaStream_t st, long long* launches);
+cudaError_t launch_krig_predict_mesh(PredictArgs a, const double* lo, const double* hi, const long long* m, long long begin,
+                                     cudaStream_t st, long long* launches);
 // host arrays lo[k], hi[k], m[k]; writes count x k doubles (points begin .. begin + count - 1 of the mesh, last dimension fastest)
 cudaError_t launch_mesh_points(const double* lo, const double* hi, const long long* m, int k, long long begin, long long count,
                                double* out, cudaStream_t st, long long* launches);

@@ -82,7 +82,13 @@ __global__ void __launch_bounds__(256) krig_predict_mean_kernel(const PredictArg
 
 // ------------------------------------------------------------------------------------ mean + MSE on DMMA
 // NTM >= NT = npad/8 (accumulator tiles kept in registers), QG query groups of 8 per warp pass.
-template <int NTM, int QG, int KD>
+// MESH: the queries are points of a full-factorial mesh.  exp(-theta_d |x_d - x_id|^p_d) then depends on (mesh coordinate
+// index, sample, dimension) only: it is tabulated once per call (sum_d m_d x n entries: 6.4 MB for the 10^4 x 10^4 mesh of
+// BASELINE config 5) and psi costs k loads + k - 1 multiplies per (query, sample) instead of k table-driven powers (46 fp64
+// instructions each) and an exp -- within k ulp of the arbitrary-point path on the generated mesh; no query coordinates are
+// read at all.  (Sum-of-terms tables + one exp per pair, bit-identical to the arbitrary-point path: 25.8 ms per 10^8 queries;
+// product form: see profiles/r02_predict_mesh.txt.)
+template <int NTM, int QG, int KD, bool MESH>
 __global__ void __launch_bounds__(256) krig_predict_mse_kernel(const PredictArgs a) {
     extern __shared__ __align__(16) double smem[];
     const int NT = a.npad / 8, k = a.k;
@@ -126,12 +132,21 @@ __global__ void __launch_bounds__(256) krig_predict_mse_kernel(const PredictArgs
         const long long q0 = pass * QW;
         // this lane's psi queries: q0 + 8 g + qrow
         double xq[QG][KD > 0 ? KD : 1];
+        const double* mrow[QG][KD > 0 ? KD : 1];  // MESH: table rows of this lane's queries, one per dimension
         long long qidx[QG];
 #pragma unroll
         for (int g = 0; g < QG; ++g) {
             qidx[g] = q0 + 8 * g + qrow;
             if (qidx[g] >= a.Nq) qidx[g] = a.Nq - 1;  // clamp: computed but never written
-            if (KD > 0) {
+            if (MESH) {
+                long long t = a.mesh_begin + qidx[g];
+#pragma unroll
+                for (int d = (KD > 0 ? KD : 1) - 1; d >= 0; --d) {
+                    const long long ix = t % a.mesh_m[d];
+                    t /= a.mesh_m[d];
+                    mrow[g][d] = a.mesh_tab + (size_t)(a.mesh_off[d] + ix) * a.npad;
+                }
+            } else if (KD > 0) {
 #pragma unroll
                 for (int d = 0; d < KD; ++d) xq[g][d] = a.Xq[qidx[g] * k + d];
             }
@@ -150,7 +165,11 @@ __global__ void __launch_bounds__(256) krig_predict_mse_kernel(const PredictArgs
 #pragma unroll
                 for (int g = 0; g < QG; ++g) {
                     double v;
-                    if (KD > 0) v = psi_one<KD>(X_s + (size_t)i * k, xq[g], th_s, p_s, k, PT);
+                    if (MESH) {  // psi = prod_d exp(-theta_d |dx_d|^p_d): the factors are tabulated
+                        v = __ldg(mrow[g][0] + i);
+#pragma unroll
+                        for (int d = 1; d < (KD > 0 ? KD : 1); ++d) v *= __ldg(mrow[g][d] + i);
+                    } else if (KD > 0) v = psi_one<KD>(X_s + (size_t)i * k, xq[g], th_s, p_s, k, PT);
                     else v = psi_one<0>(X_s + (size_t)i * k, a.Xq + qidx[g] * k, th_s, p_s, k, PT);
                     psi[g][h] = (i < a.n) ? v : 0.0;
                 }
@@ -390,21 +409,30 @@ static cudaError_t launch_mean(const PredictArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-template <int NTM, int QG, int KD>
+template <int NTM, int QG, int KD, bool MESH = false>
 static cudaError_t launch_mse_t(const PredictArgs& a, cudaStream_t st) {
     const int NT = a.npad / 8;
     const size_t smem = ((size_t)NT * (NT + 1) / 2 * 64 + (size_t)a.npad * a.k + 2 * a.npad + 2 * KMAX + 2) * 8;
-    cudaError_t e = cudaFuncSetAttribute(krig_predict_mse_kernel<NTM, QG, KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(krig_predict_mse_kernel<NTM, QG, KD, MESH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const long long npass = (a.Nq + 8 * QG - 1) / (8 * QG);
     long long grid = (npass + 7) / 8;
     const long long cap = (long long)sm_count() * 4;
     if (grid > cap) grid = cap;
-    krig_predict_mse_kernel<NTM, QG, KD><<<(int)grid, 256, smem, st>>>(a);
+    krig_predict_mse_kernel<NTM, QG, KD, MESH><<<(int)grid, 256, smem, st>>>(a);
     return cudaGetLastError();
 }
 template <int NTM, int QG>
 static cudaError_t launch_mse_k(const PredictArgs& a, cudaStream_t st) {
+    if (a.mesh_tab) {
+        switch (a.k) {
+            case 1: return launch_mse_t<NTM, QG, 1, true>(a, st);
+            case 2: return launch_mse_t<NTM, QG, 2, true>(a, st);
+            case 3: return launch_mse_t<NTM, QG, 3, true>(a, st);
+            case 4: return launch_mse_t<NTM, QG, 4, true>(a, st);
+            default: return cudaErrorInvalidValue;
+        }
+    }
     switch (a.k) {
         case 1: return launch_mse_t<NTM, QG, 1>(a, st);
         case 2: return launch_mse_t<NTM, QG, 2>(a, st);
@@ -455,6 +483,78 @@ cudaError_t launch_mesh_points(const double* lo, const double* hi, const long lo
     mesh_points_kernel<<<(int)grid, 256, 0, st>>>(ms, begin, count, out);
     if (launches) *launches += 1;
     return cudaGetLastError();
+}
+
+// mesh_tab[(off_d + ix) * npad + i] = exp(-theta_d * |axis_d[ix] - x_id| ^ p_d): psi(query, sample i) = prod_d of these factors
+// (same pow_abs / exp as psi_one, axis values as mesh_points_kernel forms them; the product of k exponentials differs from the
+// exponential of the sum by <= k ulp)
+__global__ void __launch_bounds__(256) mesh_tab_kernel(const MeshSpec ms, const double* __restrict__ X, int n, int npad,
+                                                       const double* __restrict__ theta, const double* __restrict__ p,
+                                                       long long rows, double* __restrict__ tab) {
+    __shared__ PowTables PT;
+    PT.init(threadIdx.x, blockDim.x);
+    __syncthreads();
+    const long long total = rows * npad;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t % npad);
+        long long row = t / npad;
+        int d = 0;
+        while (d + 1 < ms.k && row >= ms.m[d]) row -= ms.m[d++];
+        double v = 0.0;
+        if (i < n) {
+            double ax = ms.lo[d];
+            if (ms.m[d] > 1) {
+                const double step = (ms.hi[d] - ms.lo[d]) / (double)(ms.m[d] - 1);
+                ax = (row == ms.m[d] - 1) ? ms.hi[d] : __dadd_rn(__dmul_rn((double)row, step), ms.lo[d]);
+            }
+            v = exp_fast<false>(-__dmul_rn(theta[d], pow_abs(fabs(X[(size_t)i * ms.k + d] - ax), p[d], PT)), PT.e);
+        }
+        tab[t] = v;
+    }
+}
+
+// value (+ MSE) at points [begin, begin + Nq) of a mesh; a.Xq is ignored.  k <= 4 and n <= 128 with MSE use the tabulated
+// path, everything else generates the points and takes the arbitrary-point kernels.
+cudaError_t launch_krig_predict_mesh(PredictArgs a, const double* lo, const double* hi, const long long* m, long long begin,
+                                     cudaStream_t st, long long* launches) {
+    if (a.Nq <= 0) return cudaSuccess;
+    const int NT = a.npad / 8;
+    cudaError_t e;
+    if (a.k <= 4 && a.mse_out && NT <= 16) {
+        MeshSpec ms{};
+        ms.k = a.k;
+        long long rows = 0;
+        for (int d = 0; d < a.k; ++d) {
+            ms.lo[d] = lo[d];
+            ms.hi[d] = hi[d];
+            ms.m[d] = m[d];
+            a.mesh_m[d] = m[d];
+            a.mesh_off[d] = rows;
+            rows += m[d];
+        }
+        double* tab = nullptr;
+        e = cudaMallocAsync((void**)&tab, (size_t)rows * a.npad * 8, st);
+        if (e != cudaSuccess) return e;
+        long long grid = (rows * a.npad + 255) / 256;
+        if (grid > (long long)sm_count() * 8) grid = (long long)sm_count() * 8;
+        mesh_tab_kernel<<<(int)grid, 256, 0, st>>>(ms, a.X, a.n, a.npad, a.theta, a.p, rows, tab);
+        a.mesh_tab = tab;
+        a.mesh_begin = begin;
+        e = cudaGetLastError();
+        if (launches) *launches += 1;
+        if (e == cudaSuccess) e = launch_krig_predict(a, st, launches);
+        cudaFreeAsync(tab, st);
+        return e;
+    }
+    double* xq = nullptr;
+    e = cudaMallocAsync((void**)&xq, (size_t)a.Nq * a.k * 8, st);
+    if (e != cudaSuccess) return e;
+    e = launch_mesh_points(lo, hi, m, a.k, begin, a.Nq, xq, st, launches);
+    a.Xq = xq;
+    a.mesh_tab = nullptr;
+    if (e == cudaSuccess) e = launch_krig_predict(a, st, launches);
+    cudaFreeAsync(xq, st);
+    return e;
 }
 
 cudaError_t launch_krig_predict(const PredictArgs& a, cudaStream_t st, long long* launches) {

@@ -464,6 +464,40 @@ class Kriging:
             return y.cpu().numpy(), mse.cpu().numpy()
         return y.cpu().numpy()
 
+    def predict_mesh(self, lo, hi, m, begin=0, count=None, return_mse=True, as_device=False):
+        """Value (and MSE) at points [begin, begin + count) of the full-factorial mesh with m[d] points per dimension over
+        [lo[d], hi[d]] (last dimension fastest) -- the surface-plot meshes of the reference (examples/kriging_r3.py:59-70,
+        PlotHelper.plot_function_3d) and BASELINE config 5 -- without materialising the points: sm_krig_predict_mesh
+        tabulates the per-dimension correlation factors over the axes.  Within k ulp of predict_batch on device.mesh_points(...)."""
+        L = _cabi.lib()
+        if return_mse:
+            self._ensure_mse_state()
+        else:
+            self._ensure_fit()
+        d, f = self._dev(), self._fit
+        lo = np.ascontiguousarray(lo, dtype=np.float64)
+        hi = np.ascontiguousarray(hi, dtype=np.float64)
+        m = np.ascontiguousarray(m, dtype=np.int64)
+        count = int(np.prod(m)) - int(begin) if count is None else int(count)
+        y = device.empty(count)
+        mse = device.empty(count) if return_mse else None
+        if not f['ok']:
+            y.fill_(float('nan'))
+            if mse is not None:
+                mse.fill_(float('nan'))
+        else:
+            want_mse = return_mse and f.get('info', 0) != 3
+            _cabi.check(L.sm_krig_predict_mesh(device.ptr(d['X']), self._n, self._k, device.ptr(f['theta']), device.ptr(f['p']),
+                                               device.ptr(f['w']), f['mu'], f['sigma2'], device.ptr(f['Mop']) if want_mse else None,
+                                               device.ptr(f['b']), device.ptr(f['rres']), lo.ctypes.data, hi.ctypes.data,
+                                               m.ctypes.data, int(begin), count, device.ptr(y),
+                                               device.ptr(mse) if want_mse else None, device.stream()))
+            if return_mse and not want_mse:
+                mse.fill_(float('nan'))
+        if as_device:
+            return (y, mse) if return_mse else y
+        return (y.cpu().numpy(), mse.cpu().numpy()) if return_mse else y.cpu().numpy()
+
     def predict_device(self, xq_dev, return_mse=False):
         """predict_batch on a device tensor Xq[Nq,k]; results stay on the device (no sync)."""
         L = _cabi.lib()

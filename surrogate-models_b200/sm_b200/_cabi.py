@@ -36,6 +36,7 @@ SIGNATURES = {
     'sm_krig_predict': (_i, [_vp, _i, _i, _vp, _vp, _vp, _d, _d, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     'sm_krig_fit_predict_host': (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     'sm_mesh_points': (_i, [_vp, _vp, _vp, _i, _i64, _i64, _vp, _vp]),
+    'sm_krig_predict_mesh': (_i, [_vp, _i, _i, _vp, _vp, _vp, _d, _d, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     'sm_krig_fit_predict_mesh_host': (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp]),
     'sm_rbf_fit': (_i, [_vp, _vp, _i, _i, _i, _d, _vp, _vp, _vp]),
     'sm_rbf_predict': (_i, [_vp, _i, _i, _i, _d, _vp, _vp, _i64, _vp, _vp]),

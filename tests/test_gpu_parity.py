@@ -1020,7 +1020,10 @@ def test_chunked_host_prediction_and_mesh_entry_point(gold, K):
     _cabi.check(L.sm_krig_fit_predict_mesh_host(X.ctypes.data, y.ctypes.data, 36, 2, th.ctypes.data, p.ctypes.data,
                                                 lo.ctypes.data, hi.ctypes.data, mm.ctypes.data, 17, m * m - 17,
                                                 ym.ctypes.data, mmse.ctypes.data, sc.ctypes.data))
-    assert np.array_equal(ym, yd[17:]) and np.array_equal(mmse, md[17:])
+    # the mesh entry point tabulates per-dimension correlation factors (psi = product of k exponentials): equal to rounding
+    assert np.max(rel(ym, yd[17:])) < 1e-12 and np.max(np.abs(mmse - md[17:])) < 1e-12 * sc[2]
+    ym2, mm2 = k.predict_mesh(lo, hi, mm, begin=17)
+    assert np.array_equal(ym, ym2) and np.array_equal(mmse, mm2)                  # host entry point == device entry point
     ymean = np.empty(1000)
     _cabi.check(L.sm_krig_fit_predict_host(X.ctypes.data, y.ctypes.data, 36, 2, th.ctypes.data, p.ctypes.data, xq.ctypes.data,
                                            1000, ymean.ctypes.data, None, None))
@@ -1326,3 +1329,45 @@ def test_register_resident_kernels_grid_mode_and_loo(K, n, k_, T, P):
         km = K(np.delete(X, m, axis=0), np.delete(y, m))
         pm, im, rm = km.grid_search(T, P, return_nll=True)
         assert np.array_equal(lnll[m], rm, equal_nan=True) and guesses[m] == (pm, im)
+
+
+def test_mesh_prediction_tabulated_path(gold, K):
+    """Kriging.predict_mesh (sm_krig_predict_mesh: per-dimension correlation factors tabulated over the mesh axes) agrees with
+    predict_batch on the points device.mesh_points generates to rounding (psi as a product of k exponentials instead of one
+    exponential of a sum) -- k = 1, 2, 3, slices with an offset (bit-identical to the full run), NT up to 16, and the shapes
+    that fall back to generating the points (n > 128, k > 4, mean only: bit-identical)."""
+    from sm_b200 import device
+    rng = np.random.default_rng(5)
+    g = gold('c5_kriging_r3')
+    cases = [(g['X'], g['y'], [0.05, 0.05], [1.9, 1.9], [-2., -2.], [12., 12.], [301, 277]),
+             (g['X'][:, :1] + 0.1 * g['X'][:, 1:], g['y'], [0.3], [1.5], [-1.], [11.], [5000]),
+             (rng.uniform(0, 1, (100, 3)), None, [2., 3., 1.], [1.3, 2.0, 1.0], [0., 0., 0.], [1., 1., 1.], [37, 1, 41]),
+             (rng.uniform(0, 1, (150, 2)), None, [2., 3.], [1.3, 1.7], [0., 0.], [1., 1.], [50, 60]),          # n > 128: fallback
+             (rng.uniform(0, 1, (40, 5)), None, [1.] * 5, [1.5] * 5, [0.] * 5, [1.] * 5, [4, 3, 5, 2, 6])]      # k > 4: fallback
+    for X, y, th, p, lo, hi, m in cases:
+        if y is None:
+            y = np.sin(3 * X.sum(axis=1))
+        k = K(X, y)
+        k.update_param(th, p)
+        total = int(np.prod(m))
+        pts = device.mesh_points(lo, hi, m)
+        yb, mb = k.predict_device(pts, True)
+        ym, mm = k.predict_mesh(lo, hi, m)
+        tabulated = X.shape[1] <= 4 and X.shape[0] <= 128
+        if tabulated:
+            s2 = k._fit['sigma2']
+            assert np.max(rel(ym, yb.cpu().numpy())) < 1e-12 and np.max(np.abs(mm - mb.cpu().numpy())) < 1e-12 * s2
+        else:
+            assert np.array_equal(ym, yb.cpu().numpy()) and np.array_equal(mm, mb.cpu().numpy())
+        b0, cnt = total // 3 + 5, total // 2
+        ys, ms = k.predict_mesh(lo, hi, m, begin=b0, count=cnt)
+        assert np.array_equal(ys, ym[b0:b0 + cnt]) and np.array_equal(ms, mm[b0:b0 + cnt])
+        assert np.array_equal(k.predict_mesh(lo, hi, m, return_mse=False), k.predict_device(pts, False)[0].cpu().numpy())
+    # against the oracle on the kriging_r3 model
+    X, y = g['X'], g['y']
+    k = K(X, y)
+    k.update_param([0.05, 0.05], [1.9, 1.9])
+    ym, mm = k.predict_mesh([-2., -2.], [12., 12.], [64, 48])
+    pts = device.mesh_points([-2., -2.], [12., 12.], [64, 48]).cpu().numpy()
+    yr, mr = orc.predict_chol(X, y, [0.05, 0.05], [1.9, 1.9], pts, True)
+    assert np.max(rel(ym, yr)) < 1e-9 and np.max(np.abs(mm - mr)) < 1e-9 * k._fit['sigma2']
