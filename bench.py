@@ -442,6 +442,7 @@ def run_gpu(args):
     pred_mean_ms = timed_ms(lambda: k5.predict_device(xq, False))
     # the same mesh through the mesh entry point (per-dimension correlation factors tabulated over the axes, no coordinates read)
     mesh_ms = timed_ms(lambda: k5.predict_mesh([-2., -2.], [12., 12.], [m, m], as_device=True))
+    mesh_mean_ms = timed_ms(lambda: k5.predict_mesh([-2., -2.], [12., 12.], [m, m], return_mse=False, as_device=True))
     f_mse = 2 * n5 * 2 + 2 * n5 + n5 * n5 + 3 * n5          # 2nk + 2n + n^2 + 3n flop per query with MSE
     t_pipe = nq5 * (f_mse / P_FMA + n5 / P_EXP + 2 * n5 / P_POW)   # + n exp + n k pow on the same fp64 pipe
     f_mesh = n5 * n5 + 3 * n5 + n5                            # MSE contraction + reductions + one multiply per (query, sample)
@@ -451,7 +452,9 @@ def run_gpu(args):
                  'mesh_path': {'value': world * nq5 / (mesh_ms * 1e-3), 'unit': 'predictions/s', 'ms': mesh_ms,
                                'kernel': 'krig_predict_mse_kernel<8,2,2,MESH>', 'flops_per_query': f_mesh,
                                'frac': f_mesh * nq5 / (mesh_ms * 1e-3) / P_FMA,
-                               'hbm_gbs_achieved': nq5 * 16 / (mesh_ms * 1e-3) / 1e9},
+                               'hbm_gbs_achieved': nq5 * 16 / (mesh_ms * 1e-3) / 1e9,
+                               'mean_only_predictions_per_s': world * nq5 / (mesh_mean_ms * 1e-3),
+                               'mean_only_hbm_gbs_achieved': nq5 * 8 / (mesh_mean_ms * 1e-3) / 1e9},
                  'mean_only_predictions_per_s': world * nq5 / (pred_mean_ms * 1e-3),
                  'roofline': {'bound': 'tensor', 'bound_detail': 'fp64 pipe: n^2 DMMA contraction + n exp + n k pow per query; not HBM '
                                                                  '(32 B per query)', 'kernel': 'krig_predict_mse_kernel<8,2,2>',

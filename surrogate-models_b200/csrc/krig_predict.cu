@@ -513,6 +513,48 @@ __global__ void __launch_bounds__(256) mesh_tab_kernel(const MeshSpec ms, const 
     }
 }
 
+// mean only on a mesh: thread per query, 32 consecutive mesh points per warp.  They share every coordinate index except the
+// last dimension's, so the factors of dimensions 0 .. k-2 are warp-wide broadcasts and the last dimension's table is read
+// TRANSPOSED (tabT[i][ix]): one coalesced 256-byte request per sample.  4 instructions per (query, sample) pair.
+template <int KD>
+__global__ void __launch_bounds__(256) krig_predict_mean_mesh_kernel(const PredictArgs a, const double* __restrict__ tabT) {
+    extern __shared__ __align__(16) double smem[];
+    double* w_s = smem;  // [n]
+    for (int t = threadIdx.x; t < a.n; t += blockDim.x) w_s[t] = a.w[t];
+    __syncthreads();
+    const long long mlast = a.mesh_m[KD - 1];
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < a.Nq; q += (long long)gridDim.x * blockDim.x) {
+        long long t = a.mesh_begin + q;
+        const long long ixl = t % mlast;
+        t /= mlast;
+        const double* row[KD > 1 ? KD - 1 : 1];
+#pragma unroll
+        for (int d = KD - 2; d >= 0; --d) {
+            const long long ix = t % a.mesh_m[d];
+            t /= a.mesh_m[d];
+            row[d] = a.mesh_tab + (size_t)(a.mesh_off[d] + ix) * a.npad;
+        }
+        double acc = 0.0;
+        for (int i = 0; i < a.n; ++i) {
+            double v = __ldg(tabT + (size_t)i * mlast + ixl);
+#pragma unroll
+            for (int d = 0; d < KD - 1; ++d) v *= __ldg(row[d] + i);
+            acc = fma(v, w_s[i], acc);
+        }
+        a.y_out[q] = a.mu + acc;
+    }
+}
+// tabT[i][ix] = mesh_tab[(off_last + ix) * npad + i]
+__global__ void __launch_bounds__(256) mesh_tab_transpose_kernel(const double* __restrict__ tab, long long off, long long m, int n, int npad,
+                                                                 double* __restrict__ tabT) {
+    const long long total = (long long)n * m;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long ix = t % m;
+        const int i = (int)(t / m);
+        tabT[t] = tab[(size_t)(off + ix) * npad + i];
+    }
+}
+
 // value (+ MSE) at points [begin, begin + Nq) of a mesh; a.Xq is ignored.  k <= 4 and n <= 128 with MSE use the tabulated
 // path, everything else generates the points and takes the arbitrary-point kernels.
 cudaError_t launch_krig_predict_mesh(PredictArgs a, const double* lo, const double* hi, const long long* m, long long begin,
@@ -520,7 +562,7 @@ cudaError_t launch_krig_predict_mesh(PredictArgs a, const double* lo, const doub
     if (a.Nq <= 0) return cudaSuccess;
     const int NT = a.npad / 8;
     cudaError_t e;
-    if (a.k <= 4 && a.mse_out && NT <= 16) {
+    if (a.k <= 4 && (a.mse_out ? NT <= 16 : a.n <= 4096)) {
         MeshSpec ms{};
         ms.k = a.k;
         long long rows = 0;
@@ -542,7 +584,29 @@ cudaError_t launch_krig_predict_mesh(PredictArgs a, const double* lo, const doub
         a.mesh_begin = begin;
         e = cudaGetLastError();
         if (launches) *launches += 1;
-        if (e == cudaSuccess) e = launch_krig_predict(a, st, launches);
+        if (e == cudaSuccess && a.mse_out) e = launch_krig_predict(a, st, launches);
+        if (e == cudaSuccess && !a.mse_out) {  // mean only: last dimension's table transposed, thread per query
+            double* tabT = nullptr;
+            const long long ml = m[a.k - 1];
+            e = cudaMallocAsync((void**)&tabT, (size_t)a.n * ml * 8, st);
+            if (e == cudaSuccess) {
+                long long g2 = ((long long)a.n * ml + 255) / 256;
+                if (g2 > (long long)sm_count() * 8) g2 = (long long)sm_count() * 8;
+                mesh_tab_transpose_kernel<<<(int)g2, 256, 0, st>>>(tab, a.mesh_off[a.k - 1], ml, a.n, a.npad, tabT);
+                long long g3 = (a.Nq + 255) / 256;
+                if (g3 > (long long)sm_count() * 16) g3 = (long long)sm_count() * 16;
+                const size_t smem = (size_t)a.n * 8;
+                switch (a.k) {
+                    case 1: krig_predict_mean_mesh_kernel<1><<<(int)g3, 256, smem, st>>>(a, tabT); break;
+                    case 2: krig_predict_mean_mesh_kernel<2><<<(int)g3, 256, smem, st>>>(a, tabT); break;
+                    case 3: krig_predict_mean_mesh_kernel<3><<<(int)g3, 256, smem, st>>>(a, tabT); break;
+                    default: krig_predict_mean_mesh_kernel<4><<<(int)g3, 256, smem, st>>>(a, tabT); break;
+                }
+                e = cudaGetLastError();
+                if (launches) *launches += 2;
+                cudaFreeAsync(tabT, st);
+            }
+        }
         cudaFreeAsync(tab, st);
         return e;
     }

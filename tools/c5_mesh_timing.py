@@ -12,7 +12,11 @@ def generic():
     xs = device.mesh_points([-2., -2.], [12., 12.], [M, M]); return k.predict_device(xs, True)
 def mesh():
     return k.predict_mesh([-2., -2.], [12., 12.], [M, M], as_device=True)
-for name, fn in (('arbitrary-point kernel + device mesh', generic), ('tabulated mesh path', mesh)):
+def generic_mean():
+    xs = device.mesh_points([-2., -2.], [12., 12.], [M, M]); return k.predict_device(xs, False)
+def mesh_mean():
+    return k.predict_mesh([-2., -2.], [12., 12.], [M, M], return_mse=False, as_device=True)
+for name, fn in (('arbitrary-point kernel + device mesh', generic), ('tabulated mesh path', mesh), ('mean only, arbitrary-point kernel + device mesh', generic_mean), ('mean only, tabulated mesh path', mesh_mean)):
     fn(); torch.cuda.synchronize(); ts = []
     for _ in range(3):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
