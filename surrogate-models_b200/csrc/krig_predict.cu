@@ -544,6 +544,85 @@ __global__ void __launch_bounds__(256) krig_predict_mean_mesh_kernel(const Predi
         a.y_out[q] = a.mu + acc;
     }
 }
+// mean only on a mesh as a GEMM on DMMA.  With psi separable, the mesh of predictions is
+//     Y[row][col] = mu + sum_i A[row][i] B[col][i],   A[row][i] = w_i prod_{d < k-1} E_d[ix_d(row)][i],   B[col][i] = E_{k-1}[col][i]
+// (row = the combined index of dimensions 0 .. k-2, col = the last dimension's index): (prod_{d<k-1} m_d) x n x m_{k-1}.
+// CTA tile 128 x 128 with both operands staged in shared memory in fragment order ([k4-step][row][4]: a lane's operand is one
+// conflict-free LDS.64), 8 warps x (16 rows x 4 groups of 32 columns), 2 x 4 DMMA tiles per k-step.  36 FMA per prediction
+// at n = 36: the kernel is bound by writing the 8 bytes of each result -- the HBM-bound streamed prediction of the north star.
+constexpr int MG_TILE = 128;
+__global__ void __launch_bounds__(256) krig_predict_mean_mesh_gemm_kernel(const PredictArgs a, const long long rows_total, const int kd,
+                                                                          const long long yblock0) {
+    extern __shared__ __align__(16) double smem[];
+    const int nk4 = a.npad / 4;
+    double* As = smem;                                  // [nk4][128][4]
+    double* Bs = As + (size_t)nk4 * MG_TILE * 4;        // [nk4][128][4]
+    double* Os = Bs + (size_t)nk4 * MG_TILE * 4;        // [8 warps][16][33] output staging
+    const long long mlast = a.mesh_m[kd - 1];
+    const long long row0 = (yblock0 + blockIdx.y) * MG_TILE, col0 = (long long)blockIdx.x * MG_TILE;
+    for (int t = threadIdx.x; t < MG_TILE * a.npad; t += blockDim.x) {
+        const int i = t % a.npad, rr = t / a.npad;
+        double va = 0.0, vb = 0.0;
+        if (i < a.n) {
+            const long long row = row0 + rr, col = col0 + rr;
+            if (row < rows_total) {
+                long long rem = row;
+                va = a.w[i];
+                for (int d = kd - 2; d >= 0; --d) {
+                    const long long ix = rem % a.mesh_m[d];
+                    rem /= a.mesh_m[d];
+                    va *= a.mesh_tab[(size_t)(a.mesh_off[d] + ix) * a.npad + i];
+                }
+            }
+            if (col < mlast) vb = a.mesh_tab[(size_t)(a.mesh_off[kd - 1] + col) * a.npad + i];
+        }
+        As[((size_t)(i >> 2) * MG_TILE + rr) * 4 + (i & 3)] = va;
+        Bs[((size_t)(i >> 2) * MG_TILE + rr) * 4 + (i & 3)] = vb;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int r = lane >> 2, q = lane & 3;
+    const long long lo = a.mesh_begin, hi = a.mesh_begin + a.Nq;
+    for (int cg = 0; cg < 4; ++cg) {
+        double acc[2][4][2];
+#pragma unroll
+        for (int v = 0; v < 2; ++v)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[v][u][0] = acc[v][u][1] = 0.0;
+        for (int s = 0; s < nk4; ++s) {
+            double af[2], bf[4];
+#pragma unroll
+            for (int v = 0; v < 2; ++v) af[v] = As[((size_t)s * MG_TILE + 16 * wid + 8 * v + r) * 4 + q];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) bf[u] = Bs[((size_t)s * MG_TILE + 32 * cg + 8 * u + r) * 4 + q];
+#pragma unroll
+            for (int v = 0; v < 2; ++v)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) dmma(acc[v][u][0], acc[v][u][1], af[v], bf[u]);
+        }
+        // through a per-warp staging tile so that every store instruction writes one 256-byte row segment
+        double* ot = Os + (size_t)wid * 16 * 33;
+        __syncwarp();
+#pragma unroll
+        for (int v = 0; v < 2; ++v)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                ot[(8 * v + r) * 33 + 8 * u + 2 * q] = a.mu + acc[v][u][0];
+                ot[(8 * v + r) * 33 + 8 * u + 2 * q + 1] = a.mu + acc[v][u][1];
+            }
+        __syncwarp();
+        {
+            const long long col = col0 + 32 * cg + lane;
+#pragma unroll 4
+            for (int rr = 0; rr < 16; ++rr) {
+                const long long row = row0 + 16 * wid + rr;
+                const long long t0 = row * mlast + col;
+                if (row < rows_total && col < mlast && t0 >= lo && t0 < hi) a.y_out[t0 - lo] = ot[rr * 33 + lane];
+            }
+        }
+    }
+}
+
 // tabT[i][ix] = mesh_tab[(off_last + ix) * npad + i]
 __global__ void __launch_bounds__(256) mesh_tab_transpose_kernel(const double* __restrict__ tab, long long off, long long m, int n, int npad,
                                                                  double* __restrict__ tabT) {
@@ -585,7 +664,27 @@ cudaError_t launch_krig_predict_mesh(PredictArgs a, const double* lo, const doub
         e = cudaGetLastError();
         if (launches) *launches += 1;
         if (e == cudaSuccess && a.mse_out) e = launch_krig_predict(a, st, launches);
-        if (e == cudaSuccess && !a.mse_out) {  // mean only: last dimension's table transposed, thread per query
+        const size_t gemm_smem = ((size_t)2 * (a.npad / 4) * MG_TILE * 4 + 8 * 16 * 33) * 8;
+        if (e == cudaSuccess && !a.mse_out && gemm_smem <= smem_optin()) {  // mean only: a GEMM over (row block, column block) tiles
+            long long rows_total = 1;
+            for (int d = 0; d + 1 < a.k; ++d) rows_total *= m[d];
+            const long long ml = m[a.k - 1];
+            // blocks that intersect the requested slice [begin, begin + Nq) of the row-major mesh
+            const long long r_lo = begin / ml, r_hi = (begin + a.Nq - 1) / ml;
+            const long long by0 = r_lo / MG_TILE, by1 = r_hi / MG_TILE;
+            e = cudaFuncSetAttribute(krig_predict_mean_mesh_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem);
+            if (e == cudaSuccess) {
+                const dim3 grid((unsigned)((ml + MG_TILE - 1) / MG_TILE), (unsigned)(by1 - by0 + 1));  // blockIdx.y counts from row block by0
+                if (grid.y <= 65535) {
+                    krig_predict_mean_mesh_gemm_kernel<<<grid, 256, gemm_smem, st>>>(a, rows_total, a.k, by0);
+                    e = cudaGetLastError();
+                    if (launches) *launches += 1;
+                    cudaFreeAsync(tab, st);
+                    return e;
+                }
+            }
+        }
+        if (e == cudaSuccess && !a.mse_out) {  // mean only, general slices / large n: last dimension's table transposed, thread per query
             double* tabT = nullptr;
             const long long ml = m[a.k - 1];
             e = cudaMallocAsync((void**)&tabT, (size_t)a.n * ml * 8, st);
