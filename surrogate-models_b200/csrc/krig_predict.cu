@@ -735,6 +735,12 @@ cudaError_t launch_krig_predict(const PredictArgs& a, cudaStream_t st, long long
     }
     const int NT = a.npad / 8;
     if (NT <= 4) return launch_mse_k<4, 4>(a, st);
+    // accumulator tiles sized to the model (NTM) and 8 QG queries per warp pass, measured on the kriging_r3 model (NT = 5, 10^8
+    // mesh queries, value + MSE): <8,2> 21.3 ms, <6,2> 15.0, <5,2> 15.9, <5,3> 12.5, <6,3> 14.4, <5,4> 20.9 (tabulated mesh path);
+    // arbitrary points: <8,2> 57.9 ms, <6,2> 52.5, the three-group variants 62 .. 64
+    if (a.mesh_tab && NT <= 5) return launch_mse_k<5, 3>(a, st);
+    if (a.mesh_tab && NT <= 6) return launch_mse_k<6, 3>(a, st);
+    if (NT <= 6) return launch_mse_k<6, 2>(a, st);
     if (NT <= 8) return launch_mse_k<8, 2>(a, st);
     if (NT <= 16) return launch_mse_k<16, 1>(a, st);
     // n > 128: Psi block in shared memory, M streamed from L2 on DMMA; as many queries per block as shared memory takes
