@@ -11,7 +11,7 @@
 //   krig_rescue_kernel     one CTA per listed candidate:
 //     (a) forms R exactly as the reference does (mylibs/kriging.py:70-77): correctly rounded |dx| ** p, fp64 multiply by
 //         theta, fp64 accumulation from 0 in dimension order, correctly rounded exp -- bit-identical to the reference's
-//         matrix (glibc's pow/exp are correctly rounded in all but ~8e-4 of the calls; measured, tools/dd_check.py);
+//         matrix (glibc's pow/exp are correctly rounded in all but ~8e-4 of the calls; measured, oracle/dd_check.py);
 //     (b) factorises [R | y 1] in double-double (right-looking Cholesky on the packed lower triangle in shared memory,
 //         or in a per-CTA slice of global memory when it does not fit), mu / sigma^2 / ln det in double-double
 //         (mylibs/kriging.py:86-93,95-116 in Cholesky form);

@@ -1,6 +1,6 @@
 // Host build of csrc/dd.cuh for checking the extended-precision ("rescue") arithmetic in the build container.
 // Serial restatement of krig_rescue.cu's per-candidate algorithm with the SAME dd primitives, exported through a
-// C interface for tools/dd_check.py (ctypes).  Test tooling only.
+// C interface for oracle/dd_check.py (ctypes).  Test tooling only.
 //   g++ -O2 -ffp-contract=off -fopenmp -shared -fPIC tools/dd_check.cpp -o /tmp/libdd_check.so
 #include <cmath>
 #include <cstdlib>
