@@ -1,8 +1,8 @@
 """Dev tool: parity + timing of the n > 128 likelihood kernels (dataflow kernel vs. the macro-panel kernel).
 
-  python tools/flow_check.py                 # driver: runs every configuration in a subprocess (the kernel choice
+  python tests/devtools/flow_check.py                 # driver: runs every configuration in a subprocess (the kernel choice
                                              # is read from the environment once per process) and prints a table
-  python tools/flow_check.py worker <json>   # one configuration
+  python tests/devtools/flow_check.py worker <json>   # one configuration
 """
 import json
 import os
@@ -12,7 +12,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'surrogate-models_b200'))
 

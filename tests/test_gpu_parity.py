@@ -835,12 +835,12 @@ def test_batched_slsqp_stencil_large_n(K, capsys):
 
 
 def test_randomised_parity_sweep():
-    """tools/flow_fuzz.py: random n in [9, 700), k in [1, 8], list mode (and grid mode for small k) against the oracle;
+    """tests/devtools/flow_fuzz.py: random n in [9, 700), k in [1, 8], list mode (and grid mode for small k) against the oracle;
     the script asserts |gpu - ref| <= 1e-9 max(1, |ref|) max(1, cond / 5e6) on every well-conditioned candidate"""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, 'tools', 'flow_fuzz.py'), '3', '12'], cwd=root, capture_output=True,
+    r = subprocess.run([sys.executable, os.path.join(root, 'tests', 'devtools', 'flow_fuzz.py'), '3', '12'], cwd=root, capture_output=True,
                        text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert 'NONFINITE-MISMATCH' not in r.stdout
