@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIBDIR, 'libsurrogate_b200.so')
-SOURCES = ['capi.cu', 'krig_nll.cu', 'krig_nll_small.cu', 'krig_nll_small8.cu', 'krig_nll_n64.cu', 'krig_nll_large.cu', 'krig_nll_flow.cu', 'krig_fit.cu', 'krig_rescue.cu', 'krig_predict.cu', 'rbf.cu']
+SOURCES = ['capi.cu', 'krig_nll.cu', 'krig_nll_small.cu', 'krig_nll_small8.cu', 'krig_nll_n64.cu', 'krig_nll_large.cu', 'krig_nll_flow.cu', 'krig_nll_cta.cu', 'krig_fit.cu', 'krig_rescue.cu', 'krig_predict.cu', 'rbf.cu']
 NVCC_FLAGS = ([f'-D{d}' for d in os.environ.get('SMB_DEFINES', '').split(',') if d]) + ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC']
 

@@ -148,7 +148,7 @@ int sm_krig_nll_grid(const double* X, const double* y, int n, int k, const doubl
     // only, never on the candidate range, so shards of one grid are bit-identical to the full evaluation.
     DevBuf egrid(st);
     const size_t egrid_bytes = tper * k * P * T * 8;
-    if (!flow && npad <= 96 && k <= 4 && egrid_bytes <= ((size_t)256 << 20)) {
+    if (!flow && (npad <= 96 || nll_uses_cta(n, k)) && k <= 4 && egrid_bytes <= ((size_t)256 << 20)) {
         SM_TRY(egrid.alloc(egrid_bytes));
         SM_TRY(launch_egrid(dtab.as<double>(), theta_axis, k, P, T, t64 ? -npad : npad, egrid.as<double>(), st));
         L.n += 1;
@@ -206,7 +206,7 @@ int sm_krig_loo_grid(const double* X, const double* y, int n, int k, const doubl
         a.tab_layout = t64 ? 2 : 0;
         a.nll_out = nll_out;
         const size_t estride = dstride * T;
-        if (npad <= 96 && k <= 4 && estride * n * 8 <= ((size_t)256 << 20)) {
+        if ((npad <= 96 || nll_uses_cta(n1, k)) && k <= 4 && estride * n * 8 <= ((size_t)256 << 20)) {
             SM_TRY(egrid.alloc(estride * n * 8));
             SM_TRY(launch_egrid(dtab.as<double>(), theta_axis, k * n, P, T, t64 ? -npad : npad, egrid.as<double>(), st));
             L.n += 1;

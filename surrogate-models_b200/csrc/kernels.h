@@ -73,7 +73,9 @@ cudaError_t launch_nll_regs_10(const NllArgs& a, int mode, cudaStream_t st);
 // true when one of them takes (n, k) (33 <= n <= 80, k <= 4).  Their tables use the packed lower-triangle layout: NT (NT + 1) / 2
 // tiles of 64 doubles, lane (r, q) owning entries (8I + r, 8J + q) and (8I + r, 8J + q + 4) at doubles [2l, 2l + 1] of tile (I, J);
 // launch_dtab / launch_logtab / launch_egrid build it when called with npad NEGATED.
-bool nll_uses_regs(int n, int k, int mode);  // mode 0: grid, 1: list
+bool nll_uses_regs(int n, int k, int mode);  // mode 0: grid, 1: list; true: the caller builds packed fragment tables (tab_layout 2)
+bool nll_uses_cta(int n, int k);             // CTA-per-candidate kernel, factor in shared memory (krig_nll_cta.cu); implies nll_uses_regs
+cudaError_t launch_nll_cta(const NllArgs& a, int mode, cudaStream_t st);
 __host__ __device__ inline size_t regs_table_doubles(int npad) { return (size_t)(npad / 8) * (npad / 8 + 1) / 2 * 64; }
 cudaError_t launch_nll_large(NllArgs a, int mode, cudaStream_t st);
 cudaError_t launch_nll_flow(NllArgs a, int mode, cudaStream_t st);

@@ -882,7 +882,7 @@ bool nll_uses_flow(int n, int k) {
     // n = 96: 3.4 vs 3.8, n = 104: 2.2 vs 3.0 (k = 8), 2.1 vs 2.8 (k = 5), n = 112: 2.3 vs 3.7  ->  from n = 89
     static const int lo_env = [] { const char* v = getenv("SMB_FLOW_MIN_NT"); return v ? atoi(v) : -1; }();  // tuning / tests
     const int lo = lo_env >= 0 ? lo_env : (k > 4 ? 11 : 14);
-    return !v1 && NT > lo && (NT + 3) / 4 + 2 <= FLOW_MAXG;
+    return !v1 && NT > lo && (NT + 3) / 4 + 2 <= FLOW_MAXG && !nll_uses_cta(n, k);
 }
 
 cudaError_t launch_nll_flow(NllArgs a, int mode, cudaStream_t st) {

@@ -20,81 +20,15 @@
 // krig_nll_small_kernel, so the results are bit-identical (tools/n64_check.py, tests).
 // Shared memory keeps only the right-hand-side rows and the two 64-double scratch tiles of the diagonal factor.
 // Reference semantics: mylibs/kriging.py:53-116,130-141 per candidate; enumeration of mylibs/likeli_optimizer.py:50-97.
-#include <utility>
-
 #include "nll_small_common.cuh"
 
 namespace smb {
-
-template <class F, int... I>
-__device__ __forceinline__ void sfor_impl(F&& f, std::integer_sequence<int, I...>) {
-    (f(std::integral_constant<int, I>{}), ...);
-}
-template <int N, class F>
-__device__ __forceinline__ void sfor(F&& f) {
-    sfor_impl(f, std::make_integer_sequence<int, N>{});
-}
 
 #ifndef SMB_REGS_NT
 #define SMB_REGS_NT 8
 #endif
 constexpr int RNT = SMB_REGS_NT;                     // tile rows of the matrix
 constexpr int REGS_WARP_DOUBLES = RNT * 16 + 128;    // rhs rows | W tile | diagonal working tile
-
-// diag_factor (nll_small_common.cuh) with a filler: step j calls fill(integral_constant<j>) right after the reciprocal seed
-// of its pivot has been issued.  The filler issues independent DMMAs of the NEXT block column (its update over the block
-// columns that are already final), so the serial pivot chain -- 64 steps per candidate, ~35 % of the generic kernel's time,
-// during which this warp offers the fp64 pipe nothing -- runs underneath tensor work of the same warp.  Same arithmetic.
-template <class Fill>
-__device__ __forceinline__ bool diag_factor_fill_r(double c0, double c1, double* __restrict__ ts, double* __restrict__ wt,
-                                                 double& tp, int lane, const double tau, Fill&& fill) {
-    const int r = lane >> 2, q = lane & 3;
-    const int s = (r >> 1) & 1;
-    bool ok = true;
-    double w0 = (r == 2 * q) ? 1.0 : 0.0, w1 = (r == 2 * q + 1) ? 1.0 : 0.0;
-    ts[(2 * q) * 8 + r] = c0;
-    ts[(2 * q + 1) * 8 + r] = c1;
-    tp = 1.0;
-    double lrw_prev = 0.0;
-    const int chq = (2 * q) & 3;
-    double d = __shfl_sync(0xffffffffu, c0, 0);
-    sfor<8>([&](auto Jc) {
-        constexpr int j = decltype(Jc)::value;
-        __syncwarp();  // column j of ts and row j-1 of wt are visible
-        double wj0 = 0.0, wj1 = 0.0;
-        if constexpr (j > 0) {
-            constexpr int sj = ((j - 1) >> 1) & 1;
-            wj0 = wt[8 * (j - 1) + 2 * (chq ^ sj) + (q >> 1)];
-            wj1 = wt[8 * (j - 1) + 2 * ((chq + 1) ^ sj) + (q >> 1)];
-        }
-        const double vr = ts[j * 8 + r];
-        const double2 vc = *reinterpret_cast<const double2*>(ts + j * 8 + 2 * q);
-        ok = ok && (d > tau);
-        tp *= d;
-        const double y = rsqrt_seed(d);
-        fill(Jc);
-        const double y2 = y * y;
-        const double e = fma(-d, y2, 1.0);
-        const double inv2 = fma(y2, fma(e, e, e), y2);
-        const double t = vr * inv2;
-        c0 = fma(-t, vc.x, c0);
-        c1 = fma(-t, vc.y, c1);
-        if constexpr (j < 7) d = __shfl_sync(0xffffffffu, ((j + 1) & 1) ? c1 : c0, 4 * (j + 1) + ((j + 1) >> 1));
-        const double inv = fma(y, e * fma(0.375, e, 0.5), y);
-        if (j > 0 && r > j - 1) {
-            w0 = fma(-lrw_prev, wj0, w0);
-            w1 = fma(-lrw_prev, wj1, w1);
-        }
-        lrw_prev = vr * inv;
-        if (r == j) {
-            wt[8 * r + 2 * (chq ^ s) + (q >> 1)] = w0 * inv;
-            wt[8 * r + 2 * ((chq + 1) ^ s) + (q >> 1)] = w1 * inv;
-        }
-        if (j < 7 && q == ((j + 1) >> 1)) ts[(j + 1) * 8 + r] = ((j + 1) & 1) ? c1 : c0;
-    });
-    __syncwarp();
-    return ok;
-}
 
 // 4 warps per CTA; 3 CTAs per SM at 168 registers up to NT = 8 (8 warps x 254 registers: -1 %, 16 x 128 with spills: +4 %,
 // measured at NT = 8), 2 CTAs at 254 registers above (up to 25 live tiles + 10 accumulator pairs)

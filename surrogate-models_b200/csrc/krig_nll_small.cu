@@ -418,12 +418,14 @@ bool nll_uses_regs(int n, int k, int mode) {
     // measured (profiles/r02_regs_kernel_sizes.txt): grid mode +10 .. +42 % over the shared-memory kernel for every NT = 5 .. 10,
     // list mode +10 .. +15 % at k = 2; list mode with k = 4 at NT = 10 is 7 % slower (exp per entry and dimension on top of
     // 25 live tiles), so list mode above NT = 8 keeps the shared-memory kernel for k >= 3
+    if (nll_uses_cta(n, k)) return true;  // same tables, factor in shared memory (krig_nll_cta.cu)
     if (mode == 1 && NT > 8 && k >= 3) return false;
     return !off && NT >= 5 && NT <= 10 && k >= 1 && k <= 4 && !nll_uses_flow(n, k);
 }
 
 cudaError_t launch_nll_small(const NllArgs& a, int mode, cudaStream_t st) {
     const int NT = a.npad / 8;
+    if (a.tab_layout == 2 && NT > 10) return launch_nll_cta(a, mode, st);
     if (a.k > 8 || NT > 18 || a.C <= 0) return cudaErrorNotSupported;
     // npad = 64, k <= 4: the statically unrolled kernel (krig_nll_n64.cu; SMB_N64_OFF=1 keeps the generic one, used by the
     // cross-check in the tests -- the two are bit-identical)

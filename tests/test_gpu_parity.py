@@ -1376,3 +1376,85 @@ def test_mesh_prediction_tabulated_path(gold, K):
     pts = device.mesh_points([-2., -2.], [12., 12.], [64, 48]).cpu().numpy()
     yr, mr = orc.predict_chol(X, y, [0.05, 0.05], [1.9, 1.9], pts, True)
     assert np.max(rel(ym, yr)) < 1e-9 and np.max(np.abs(mm - mr)) < 1e-9 * k._fit['sigma2']
+
+
+# ------------------------------------------------------------------------------------------ CTA-per-candidate kernel (97 <= n <= 176, k <= 2)
+@pytest.mark.parametrize('n,k_', [(97, 2), (100, 1), (104, 2), (111, 2), (120, 1), (128, 2), (129, 2), (137, 1), (150, 2), (168, 2), (176, 1), (176, 2)])
+def test_cta_kernel_both_modes_against_oracle(K, n, k_):
+    """krig_nll_cta.cu (factor resident in shared memory, 8 warps share a candidate): tile counts NT = 13 .. 22 cover its three
+    instantiations and every remainder of the 8-warp row split; list mode (p = 2 and p = 1 rows, a candidate that is not
+    numerically positive definite) and grid mode (first-minimum index, sampled values) against the oracle"""
+    rng = np.random.default_rng(n * 10 + k_)
+    X = rng.uniform(0, 10, (n, k_))
+    y = np.sin(X.sum(axis=1)) + 0.1 * X[:, 0] ** 2
+    C = 900                            # more candidates than resident CTAs (2 per SM): every CTA loops over candidates
+    e = rng.uniform(-1.5, 0.3, (C, k_)) if k_ > 1 else rng.uniform(0.3, 1.5, (C, 1))   # 1-D: dense points, larger theta
+    p = rng.uniform(1, 2, (C, k_))
+    p[0], p[1] = 2.0, 1.0
+    e[2] = -9.0                        # R ~ all ones: fails in fp64 (CTA-wide early exit), re-evaluated in double-double; the
+                                       # candidates after it in the same CTA are unaffected
+    k = K(X, y)
+    nll = k.likelihood_batch(e, p)
+    idx = np.concatenate([np.arange(6), rng.choice(C, size=10, replace=False), [C - 1]])
+    ref = np.array([orc.nll_chol(X, y, 10. ** e[c], p[c]) for c in idx])
+    cond = np.array([orc.cond2(orc.corr_matrix(X, 10. ** e[c], p[c])) for c in idx])
+    assert check_values(nll[idx], ref, cond, cond_max=1e11) >= 8     # tol() widens with the condition number
+    assert not np.isnan(nll[2])
+    T, P = 6, 3
+    param, bi, g = k.grid_search(T, P, return_nll=True)
+    eg, pg = orc.grid_candidates(k_, T, P)
+    gi = rng.choice(len(g), size=min(8, len(g)), replace=False)
+    rg = np.array([orc.nll_chol(X, y, 10. ** eg[c], pg[c]) for c in gi])
+    cg = np.array([orc.cond2(orc.corr_matrix(X, 10. ** eg[c], pg[c])) for c in gi])
+    check_values(g[gi], rg, cg)
+    fin = np.where(np.isfinite(g), g, np.inf)
+    assert bi == int(np.argmin(fin))   # first strict minimum, as the reference's scan
+
+
+def test_cta_kernel_cross_check_and_model_dimension(K):
+    """(a) SMB_CTA_MAX_NT=0 restores the previous routing (warp-per-candidate / dataflow kernels): same values within the
+    conditioning tolerance on a list and a grid; (b) the leave-one-out batch at n - 1 = 120 runs n sample sets through the
+    kernel's model dimension in one launch: rows equal the single-set grids"""
+    import json
+    import subprocess
+    import sys
+    script = r'''
+import json, os, sys
+import numpy as np
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), 'surrogate-models_b200'))
+from mylibs.kriging import Kriging
+rng = np.random.default_rng(77)
+out = {}
+for n in (112, 160):
+    X = rng.uniform(0, 10, (n, 2)); y = np.sin(X.sum(axis=1)) + 0.1 * X[:, 0] ** 2
+    e = rng.uniform(-1.2, 0.3, (400, 2)); p = rng.uniform(1, 2, (400, 2))
+    kr = Kriging(X, y)
+    out['l%d' % n] = [float(v) for v in kr.likelihood_batch(e, p)]
+    out['g%d' % n] = [None if not np.isfinite(v) else float(v) for v in kr.likelihood_grid(5, 4)[2].cpu().numpy()]
+print(json.dumps(out))
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for flag in ('22', '0'):
+        env = dict(os.environ, SMB_CTA_MAX_NT=flag)
+        r = subprocess.run([sys.executable, '-c', script], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[flag] = json.loads(r.stdout.strip().split('\n')[-1])
+    for key in res['0']:
+        a = np.array([np.nan if v is None else v for v in res['22'][key]])
+        b = np.array([np.nan if v is None else v for v in res['0'][key]])
+        m = np.isfinite(a) & np.isfinite(b)
+        assert m.sum() >= 0.9 * len(a), key
+        # candidates of these ranges have cond <= ~1e9: both routes are within tol(cond) of the oracle, so within 2 tol of each other
+        assert np.max(rel(a[m], b[m])) < 4e-7, (key, np.max(rel(a[m], b[m])))
+        assert np.median(rel(a[m], b[m])) < 1e-12, key
+    rng = np.random.default_rng(3)
+    X = rng.uniform(0, 10, (121, 2))
+    y = np.sin(X.sum(axis=1))
+    k = K(X, y)
+    n0 = _cabi.launch_count()
+    guesses, nll = k.loo_grid_guesses(4, 3, return_nll=True)
+    assert _cabi.launch_count() - n0 <= 8 and nll.shape == (121, 144)
+    for m in (0, 60, 120):
+        param, idx, ref = K(np.delete(X, m, axis=0), np.delete(y, m)).grid_search(4, 3, return_nll=True)
+        assert np.array_equal(nll[m], ref, equal_nan=True) and guesses[m] == (param, idx)
