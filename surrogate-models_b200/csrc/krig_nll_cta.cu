@@ -1,24 +1,30 @@
-// CTA-per-candidate likelihood kernel with the FACTOR RESIDENT IN SHARED MEMORY, 81 <= n (npad = 8 NT, NT >= 11), k <= 4.
-// Fills the hole between the register-resident warp-per-candidate kernels (krig_nll_regs.cu, n <= 80) and the sizes where
-// the L2-streamed dataflow kernel (krig_nll_flow.cu) reaches its stride.
+// CTA-per-candidate likelihood kernel with the FACTOR RESIDENT IN SHARED MEMORY: 97 <= n <= 176 (NT = 13 .. 22 tile rows), k <= 2.
+// Sits between the register-resident warp-per-candidate kernels (krig_nll_regs.cu, n <= 80; krig_nll_small.cu up to n = 96)
+// and the sizes where the L2-streamed dataflow kernel (krig_nll_flow.cu) reaches its stride.
 //
-// Why a CTA per candidate: a warp-per-candidate kernel at these sizes keeps 36 - 48 KB of tiles per WARP (4 - 5 warps per SM),
-// and every block column is one warp's serial chain.  Here the W warps of a CTA share one factor:
-//   * tile row I belongs to warp I mod W (the right-hand-side rows y^T / 1^T to warp NT mod W), so every k-step of a block
-//     column is spread over the warps and a warp needs only ceil(NT / W) accumulator tiles;
-//   * the 8x8 diagonal tile J is factored by its owner (warp J mod W) while the OTHER warps already run the k-steps K < J of
-//     block column J + 1 (look-ahead; the owner issues its share of them as the filler of its pivot steps), so the serial
-//     pivot chain of the CTA runs under tensor work of the same candidate;
+// A warp-per-candidate kernel keeps 36 - 48 KB of tiles per WARP at these sizes (4 - 5 warps per SM) and every block column is
+// one warp's serial program.  Here the W = 8 warps of a CTA share one candidate:
+//   * tile row I belongs to warp I mod W (the right-hand-side rows y^T / 1^T to warp NT mod W): every k-step of a block column
+//     is spread over the warps, a warp holds ceil(NT / W) <= 3 accumulator tiles;
+//   * the 8x8 diagonal tile J is factored by its owner (warp J mod W) while the OTHER warps run the k-steps K < J of block
+//     column J + 1 (look-ahead).  The owner's share of that look-ahead is caught up at the top of the next iteration, where it
+//     is not the owner; the owner of tile J + 1 takes its k-step K = J straight from the registers of its panel solve, so the
+//     next diagonal tile never waits for a shared-memory round trip;
 //   * LIVE-RANGE PACKING of the strictly-lower tiles: tile (I, K) is created in block column K and last read in block column
-//     I, so the band a = I - K - 1 needs a ring of min(a + 2, NT - 1 - a) slots -- NT^2/4 + O(NT) slots instead of
-//     NT^2/2: 71 at NT = 16 (36 KB, 5 CTAs per SM), 271 at NT = 32 (139 KB).  Slot offsets come from a 16-bit table in
-//     shared memory filled once per CTA.
+//     I, so the band a = I - K - 1 needs a ring of min(a + 2, NT - 1 - a) slots -- NT^2/4 + O(NT) slots instead of NT^2/2:
+//     71 at NT = 16 (36 KB per candidate), 155 at NT = 24.  Slot offsets come from a 16-bit table in shared memory filled once
+//     per CTA.
 // Tiles are kept in A-operand fragment order (lane (r, q) owns T[r][q], T[r][q+4] as one 16-byte chunk) and the B operand is
 // the same tile with its rows permuted by sigma = [0,4,1,5,2,6,3,7] (krig_nll_regs.cu): accumulators then come out of
 // mma.m8n8k4 as A-operand fragments, a finished tile is ONE conflict-free STS.128 per lane and every operand ONE LDS.128
 // (chunk position (4r + q) ^ (4 (r >> 2)) makes both the natural and the permuted read conflict-free).
 // Tables: the packed fragment layout of the register-resident kernels (kernels.h: tab_layout 2, regs_table_doubles).
 // Two __syncthreads per block column: W_J published -> panel solve; panel tiles stored -> k-step K = J of column J + 1.
+// The k-loops are instantiated per (tile count of the warp, diagonal tile among them, right-hand-side rows) -- all warp-uniform
+// -- and the warp index is taken through a shuffle so the compiler KNOWS it is uniform: without that every mma.sync sat behind
+// predication + reconvergence barriers (100 k instead of 43 k instructions per candidate at n = 128, profiles/r02_cta_kernel.md).
+// Measured and rejected (same file): 4 or 16 warps per CTA, counters in shared memory instead of the two barriers (a dataflow
+// like krig_nll_flow.cu: -5 %), a diagonal tile factored redundantly in every lane (no communication per pivot: -10 %).
 // Reference semantics: mylibs/kriging.py:53-116,130-141 per candidate; enumeration of mylibs/likeli_optimizer.py:50-97.
 #include <cstdlib>
 
