@@ -536,7 +536,9 @@ def run_gpu(args):
     secondary_c3 = dict(c3pt, metric='kriging likelihood evaluations/s (n=1024, k=8, list mode)',
                         kernel='krig_nll_flow_kernel<6,3,1,2> (dataflow kernel, every n > 144; <4,2,1,4> below n = 1024)',
                         other_sizes=[large_n_point(256, 9472), large_n_point(512, 2368), large_n_point(2048, 296)],
-                        grid_mode=large_n_grid_point(1024, 3, 8, 3))
+                        grid_mode=large_n_grid_point(1024, 3, 8, 3),
+                        # n = 128, k = 2: the CTA-per-candidate kernel with the factor in shared memory (krig_nll_cta.cu)
+                        mid_n_grid_mode=large_n_grid_point(128, 2, 20, 10))
     # strong scaling of north-star config 3: 1e5 candidates IN TOTAL split over the ranks through the product API
     # (Kriging.likelihood_batch(distributed=...): H2D of this rank's rows, kernel, 16-byte argmin all_gather; results stay sharded)
     X3s, y3s = workloads.c3_lhs1024()

@@ -43,7 +43,7 @@ const char* sm_b200_error_string(int code);
 /* kernels launched by this library since load (bench.py's gpu_launches) */
 long long sm_b200_launch_count(void);
 /* Scratch (tables, tile workspaces) comes from the device's default stream-ordered memory pool, which keeps up to
- * SMB_POOL_KEEP_MB (environment, default 2048) cached between calls; sm_b200_trim_pool() synchronises the device and
+ * SMB_POOL_KEEP_MB (environment; default a quarter of the device memory, at most 32 GB) cached between calls; sm_b200_trim_pool() synchronises the device and
  * returns all cached scratch to the driver. */
 int sm_b200_trim_pool(void);
 /* theta = 10 ** e element-wise, correctly rounded -- the reference forms theta with libm's pow(10., e)

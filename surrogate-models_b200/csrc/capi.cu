@@ -42,11 +42,14 @@ void keep_pool_cached() {
     if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        // keep up to SMB_POOL_KEEP_MB (default 2048) of freed scratch cached in the pool; anything above goes back to the
-        // driver at the next synchronisation, so a caching allocator next door (PyTorch) is not starved.
-        // sm_b200_trim_pool() releases the rest on demand.
-        unsigned long long thr = 2048ull << 20;
-        if (const char* v = getenv("SMB_POOL_KEEP_MB")) thr = (unsigned long long)atoll(v) << 20;
+        // keep up to SMB_POOL_KEEP_MB of freed scratch cached in the pool (default: a quarter of the device memory, at most
+        // 32 GB); anything above goes back to the driver at the next synchronisation, so a caching allocator next door
+        // (PyTorch) is not starved.  sm_b200_trim_pool() releases the rest on demand.  The default has to cover the
+        // workspaces of the dataflow likelihood kernel (2.5 GB at n = 1024, 10 GB at n = 2048): with the first setting of 2 GB
+        // every call re-allocated them from the driver -- 21 -> 69 ms per 1 184 candidates at n = 1024 (bench, secondary_c3).
+        unsigned long long thr = 32ull << 30;
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b / 4 < thr) thr = total_b / 4;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
     done_for = dev;
