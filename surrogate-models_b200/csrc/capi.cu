@@ -157,19 +157,6 @@ int sm_krig_nll_grid(const double* X, const double* y, int n, int k, const doubl
         L.n += 1;
         a.egrid = egrid.as<double>();
     }
-    // dataflow kernel, k <= 4: the same product form on its tile-packed tables (its entry tasks then multiply k table values
-    // instead of evaluating an exponential per entry: 26 % of the kernel's warp-cycles at n = 256).  Up to 512 MB of tables, and
-    // only for grids with enough candidates per table to pay for building them.
-    const size_t fper = flow_table_doubles(n), fbytes = fper * k * P * T * 8;
-    static const bool flow_egrid_off = [] { const char* v = getenv("SMB_FLOW_EGRID_OFF"); return v && v[0] == '1'; }();
-    double grid_total = 1.0;  // T^k P^k: the choice depends on the grid, never on the candidate range (shards stay bit-identical)
-    for (int d = 0; d < k; ++d) grid_total *= (double)T * P;
-    if (flow && !flow_egrid_off && k <= 4 && fbytes <= ((size_t)512 << 20) && fper * k * P * T < ((size_t)1 << 32) && grid_total >= 4.0 * k * P * T) {
-        SM_TRY(egrid.alloc(fbytes));
-        SM_TRY(launch_egrid_per(dtab.as<double>(), theta_axis, k, P, T, fper, egrid.as<double>(), st));
-        L.n += 1;
-        a.egrid = egrid.as<double>();
-    }
     SM_TRY(launch_nll(a, 0, st, &L.n));
     if (best_val && best_idx) {
         SM_TRY(launch_argmin(nll_out, c_count, c_begin, best_val, (long long*)best_idx, st));

@@ -89,7 +89,6 @@ cudaError_t launch_dtab(const double* X, int n, int k, int npad, const double* p
 cudaError_t launch_loo_gather(const double* X, const double* y, int n, int k, double* Xm, double* ym, cudaStream_t st);
 cudaError_t launch_argmin_segments(const double* v, long long seg, int nseg, double* best_val, long long* best_idx, cudaStream_t st);
 cudaError_t launch_egrid(const double* dtab, const double* theta_axis, int k, int P, int T, int npad, double* E, cudaStream_t st);
-cudaError_t launch_egrid_per(const double* dtab, const double* theta_axis, int k, int P, int T, size_t per, double* E, cudaStream_t st);
 cudaError_t launch_logtab(const double* X, int n, int k, int npad, double* LG, cudaStream_t st);
 cudaError_t launch_argmin(const double* v, long long C, long long c_begin, double* best_val, long long* best_idx,
                           cudaStream_t st);

@@ -459,11 +459,7 @@ cudaError_t launch_argmin_segments(const double* v, long long seg, int nseg, dou
     return cudaGetLastError();
 }
 cudaError_t launch_egrid(const double* dtab, const double* theta_axis, int k, int P, int T, int npad, double* E, cudaStream_t st) {
-    return launch_egrid_per(dtab, theta_axis, k, P, T, npad > 0 ? (size_t)npad * npad : regs_table_doubles(-npad), E, st);
-}
-// per = doubles of one table (any layout: the product-form table is elementwise in the |dx|^p table)
-cudaError_t launch_egrid_per(const double* dtab, const double* theta_axis, int k, int P, int T, size_t per, double* E, cudaStream_t st) {
-    const size_t ntab = (size_t)k * P;
+    const size_t per = npad > 0 ? (size_t)npad * npad : regs_table_doubles(-npad), ntab = (size_t)k * P;
     size_t blocks = (ntab * T * per + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
     egrid_kernel<<<(int)blocks, 256, 0, st>>>(dtab, theta_axis, T, per, ntab, E);

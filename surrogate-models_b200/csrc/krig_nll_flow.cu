@@ -132,9 +132,6 @@ struct FlowGeom {
 // one dimension as ONE coalesced 512-byte request (the row-major table cost 8 separate 64-byte pieces per request).
 //   MODE 1 (list): tab[(tri * k + d) * 64 + 2l] = 512 log2|dx_d|          off[d] = 64 d,  tstride = 64 k
 //   MODE 0 (grid): tab[((d * P + q) * ntri + tri) * 64 + 2l] = |dx_d|^p_q  off[d] selects (d, q_d), tstride = 64
-//   MODE 2 (grid, k <= 4, product form): tab[(((d * P + q) * T + t) * ntri + tri) * 64 + 2l] = exp(-theta_t |dx_d|^p_q)  (egrid_kernel);
-//           off[d] selects (d, q_d, t_d); an entry is the product of k table values -- no exponential at all in the kernel.
-//           (tools/phase_timing_flow.py: the entry tasks were 26 % of all warp-cycles at n = 256 and 23 % at n = 512 in grid mode.)
 // A chunk = 4 dimensions x 2 entries is evaluated as ONE straight-line block so the 8 independent powers interleave.
 // Dimensions k .. 4 ceil(k/4) - 1 run with weight 0 (the per-candidate parameter arrays are padded).
 // Register pipeline without copies: a chunk first reduces its 8 table values to what the rest of the evaluation needs
@@ -158,7 +155,6 @@ __device__ __forceinline__ void flow_e_loop(const FlowCtl& S, const FlowGeom& G,
 #define FLOW_E_NBUF_GRID 1
 #endif
     constexpr int NBUF = (MODE == 0) ? FLOW_E_NBUF_GRID : 1;
-    const int kk = (MODE == 2) ? nch : 0;  // MODE 2: nch carries k (one chunk per tile)
     const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52, as in pow2_fast
     // tile cursors (ii, jj) of the block -- diagonal block: the 10 lower tiles row by row; ii == 4: past the end
     auto advance = [&](int& ii, int& jj) {
@@ -176,11 +172,7 @@ __device__ __forceinline__ void flow_e_loop(const FlowCtl& S, const FlowGeom& G,
                 const unsigned I = 4 * g + min(lii, nrow - 1), J = 4 * b + min(ljj, ncol - 1);  // clamped: always a real tile
                 lbase = (I * (I + 1) / 2 + J) * tstride;
             }
-            if (MODE == 2) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (u < kk) buf[u] = __ldg(reinterpret_cast<const double2*>(tab + (size_t)(lbase + S.off[u])));
-            } else if (MODE == 1 && dense) {  // k % 4 == 0: the four dimensions of a chunk are 64 doubles apart, one address
+            if (MODE == 1 && dense) {  // k % 4 == 0: the four dimensions of a chunk are 64 doubles apart, one address
                 const double2* src = reinterpret_cast<const double2*>(tab + (size_t)(lbase + 256u * (unsigned)lch));
 #pragma unroll
                 for (int u = 0; u < 4; ++u) buf[u] = __ldg(src + 32 * u);
@@ -188,26 +180,13 @@ __device__ __forceinline__ void flow_e_loop(const FlowCtl& S, const FlowGeom& G,
 #pragma unroll
                 for (int u = 0; u < 4; ++u) buf[u] = __ldg(reinterpret_cast<const double2*>(tab + (size_t)(lbase + S.off[4 * lch + u])));
             }
-            if (MODE == 2 || ++lch == nch) {
+            if (++lch == nch) {
                 lch = 0;
                 advance(lii, ljj);
             }
         }
     };
     auto chunk = [&](double2 (&buf)[4]) {
-        if (MODE == 2) {  // product of the k table values; the tile is complete after its one chunk
-            double p0 = buf[0].x, p1 = buf[0].y;
-#pragma unroll
-            for (int u = 1; u < 4; ++u)
-                if (u < kk) {
-                    p0 *= buf[u].x;
-                    p1 *= buf[u].y;
-                }
-            issue(buf);
-            if (cii < nrow && cjj < ncol) *reinterpret_cast<double2*>(slots + G.tile_off(4 * g + cii, 4 * b + cjj)) = make_double2(p0, p1);
-            advance(cii, cjj);
-            return;
-        }
         double t0[4], t1[4], r0[4], r1[4];
         double a0 = 0.0, a1 = 0.0;  // second partial sum per entry: shorter dependent chains
         if (MODE == 1) {
@@ -265,7 +244,7 @@ __device__ __forceinline__ void flow_e_loop(const FlowCtl& S, const FlowGeom& G,
     double2 buf[NBUF][4];
 #pragma unroll
     for (int i = 0; i < NBUF; ++i) issue(buf[i]);
-    const int total = ntile * (MODE == 2 ? 1 : nch);
+    const int total = ntile * nch;
 #pragma unroll 1
     for (int x = 0; x < total; x += NBUF) {
 #pragma unroll
@@ -278,12 +257,12 @@ template <int MODE>
 __device__ __forceinline__ void flow_task_e(const FlowCtl& S, const NllArgs& a, double* __restrict__ tiles, const int b,
                                             const int g, const int lane) {
     const FlowGeom G(a);
-    const double* const tab = (MODE == 0 ? a.dtab : (MODE == 2 ? a.egrid : a.log2tab)) + 2 * lane;
-    const unsigned tstride = (MODE == 1) ? 64u * (unsigned)a.k : 64u;
-    const int nch = (MODE == 2) ? a.k : (a.k + 3) >> 2;
+    const double* const tab = (MODE == 0 ? a.dtab : a.log2tab) + 2 * lane;
+    const unsigned tstride = (MODE == 0) ? 64u : 64u * (unsigned)a.k;
+    const int nch = (a.k + 3) >> 2;
     double* const slots = tiles + 2 * lane;
     const bool dense = (a.k & 3) == 0;
-    if (MODE != 1 || S.safe_p != 0) flow_e_loop<MODE, true>(S, G, tab, tstride, nch, dense, slots, b, g);
+    if (MODE == 0 || S.safe_p != 0) flow_e_loop<MODE, true>(S, G, tab, tstride, nch, dense, slots, b, g);
     else flow_e_loop<MODE, false>(S, G, tab, tstride, nch, dense, slots, b, g);
 }
 
@@ -649,7 +628,7 @@ __global__ void __launch_bounds__(LW * 32, CPS) krig_nll_flow_kernel(const NllAr
             const int d = min((int)threadIdx.x, a.k - 1);
             const bool real = (int)threadIdx.x < a.k;
             const double LOG2E = 1.4426950408889634;
-            if (MODE != 1) {
+            if (MODE == 0) {
                 long long tk = 1;
                 for (int e = 0; e < a.k; ++e) tk *= a.T;
                 const long long cg = a.c_begin + c;
@@ -660,8 +639,7 @@ __global__ void __launch_bounds__(LW * 32, CPS) krig_nll_flow_kernel(const NllAr
                 }
                 S.th2[threadIdx.x] = real ? a.theta_axis[it % a.T] * LOG2E : 0.0;
                 S.pw[threadIdx.x] = 1.0;
-                S.off[threadIdx.x] = (MODE == 2) ? (unsigned)((((long long)d * a.P + (ip % a.P)) * a.T + (it % a.T)) * (long long)ntri * 64)
-                                                 : (unsigned)(((long long)d * a.P + (ip % a.P)) * (long long)ntri * 64);
+                S.off[threadIdx.x] = (unsigned)(((long long)d * a.P + (ip % a.P)) * (long long)ntri * 64);
             } else {
                 S.th2[threadIdx.x] = real ? a.theta[c * a.k + d] * LOG2E : 0.0;
                 S.pw[threadIdx.x] = real ? a.p[c * a.k + d] : 1.0;
@@ -847,7 +825,7 @@ static cudaError_t launch_flow_t(NllArgs a, int mode, cudaStream_t st) {
     const int NT = a.npad / 8;
     const size_t tile_bytes = flow_ws_doubles(NT) * 8;
     const size_t smem = (size_t)LW * ST * 8 * 512;
-    auto kern = (mode == 0) ? (a.egrid ? krig_nll_flow_kernel<LW, ST, 2, CPS> : krig_nll_flow_kernel<LW, ST, 0, CPS>) : krig_nll_flow_kernel<LW, ST, 1, CPS>;
+    auto kern = (mode == 0) ? krig_nll_flow_kernel<LW, ST, 0, CPS> : krig_nll_flow_kernel<LW, ST, 1, CPS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     // carve out what CPS resident CTAs need (static + dynamic + 1 KB reserved each) and leave the rest to L1, which
@@ -913,7 +891,7 @@ cudaError_t launch_nll_flow(NllArgs a, int mode, cudaStream_t st) {
     if (mode == 1 && !a.log2tab) return cudaErrorInvalidValue;
     {   // the entry tasks index the tables with 32-bit offsets (doubles)
         const size_t nt = (size_t)(a.npad / 8), ntri = nt * (nt + 1) / 2;
-        const size_t tab_doubles = ntri * 64 * (size_t)a.k * (size_t)(mode == 0 ? a.P : 1) * (size_t)(mode == 0 && a.egrid ? a.T : 1);
+        const size_t tab_doubles = ntri * 64 * (size_t)a.k * (size_t)(mode == 0 ? a.P : 1);
         if (tab_doubles >= ((size_t)1 << 32)) return cudaErrorInvalidValue;
     }
     cudaError_t e = upload_e2tab();

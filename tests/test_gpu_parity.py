@@ -1458,54 +1458,3 @@ print(json.dumps(out))
     for m in (0, 60, 120):
         param, idx, ref = K(np.delete(X, m, axis=0), np.delete(y, m)).grid_search(4, 3, return_nll=True)
         assert np.array_equal(nll[m], ref, equal_nan=True) and guesses[m] == (param, idx)
-
-
-# ------------------------------------------------------------------------------------------ dataflow kernel, product-form entry tables
-@pytest.mark.parametrize('n,k_,T,P', [(200, 2, 9, 5), (257, 3, 5, 3), (300, 4, 3, 2), (520, 2, 7, 4)])
-def test_dataflow_kernel_product_form_tables(K, n, k_, T, P):
-    """grid mode of krig_nll_flow.cu with k <= 4: R_ij = prod_d exp(-theta_t |dx_d|^p_q) from tabulated factors (no exponential
-    per entry in the kernel).  Against the oracle on sampled candidates and against the exp-per-entry form (SMB_FLOW_EGRID_OFF=1
-    in a subprocess) on every candidate, within the conditioning tolerance; same first minimum; sharded ranges bit-identical"""
-    import json
-    import subprocess
-    import sys
-    rng = np.random.default_rng(n + k_)
-    X = rng.uniform(0, 10, (n, k_))
-    y = np.sin(X.sum(axis=1)) + 0.1 * X[:, 0] ** 2
-    k = K(X, y)
-    param, bi, g = k.grid_search(T, P, return_nll=True)
-    C = len(g)
-    assert C >= 4 * k_ * P * T                         # the product form is used from this many candidates on
-    eg, pg = orc.grid_candidates(k_, T, P)
-    idx = rng.choice(C, size=10, replace=False)
-    ref = np.array([orc.nll_chol(X, y, 10. ** eg[c], pg[c]) for c in idx])
-    cond = np.array([orc.cond2(orc.corr_matrix(X, 10. ** eg[c], pg[c])) for c in idx])
-    assert check_values(g[idx], ref, cond, cond_max=1e11) >= 3
-    fin = np.where(np.isfinite(g), g, np.inf)
-    assert bi == int(np.argmin(fin))
-    half = C // 2 + 1                                  # a shard of the same grid: the table form depends on the grid, not the range
-    _, _, g1 = k.likelihood_grid(T, P, half, C - half)
-    assert np.array_equal(g1.cpu().numpy(), g[half:], equal_nan=True)
-    script = r'''
-import json, os, sys
-import numpy as np
-sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), 'surrogate-models_b200'))
-from mylibs.kriging import Kriging
-n, k_, T, P = (int(v) for v in sys.argv[1:5])
-rng = np.random.default_rng(n + k_)
-X = rng.uniform(0, 10, (n, k_)); y = np.sin(X.sum(axis=1)) + 0.1 * X[:, 0] ** 2
-g = Kriging(X, y).likelihood_grid(T, P)[2].cpu().numpy()
-print(json.dumps([None if not np.isfinite(v) else float(v) for v in g]))
-'''
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, '-c', script, str(n), str(k_), str(T), str(P)], cwd=root, env=dict(os.environ, SMB_FLOW_EGRID_OFF='1'),
-                       capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stderr[-2000:]
-    e = np.array([np.nan if v is None else v for v in json.loads(r.stdout.strip().split('\n')[-1])])
-    m = np.isfinite(e) & np.isfinite(g)
-    assert m.sum() >= 0.5 * C
-    d = rel(g[m], e[m])
-    assert np.median(d) < 1e-11, np.median(d)
-    # the two forms differ by rounding in the entries (~1e-16 relative), amplified by the condition number
-    ms = np.isfinite(e[idx]) & np.isfinite(g[idx]) & (cond <= 1e11)
-    assert np.all(rel(g[idx][ms], e[idx][ms]) <= 2 * tol(cond[ms]))
