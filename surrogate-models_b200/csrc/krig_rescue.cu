@@ -65,6 +65,11 @@ __global__ void __launch_bounds__(THREADS) krig_rescue_kernel(const NllArgs a, c
     double* pw = th + KMAX;                        // [KMAX]
     size_t* toff = reinterpret_cast<size_t*>(pw + KMAX);  // [KMAX] offset of table (d, q_d) in a.dtab
     dd* A = ws_stride ? gws + (size_t)blockIdx.x * ws_stride : reinterpret_cast<dd*>(toff + KMAX);
+    // matrix in global memory (n > ~165): the scaled current column is mirrored in shared memory, so an element of the trailing
+    // update costs one L2 load + one store instead of three loads + one store, and four elements are in flight per thread
+    // (n = 256, 623 flagged candidates of a 40 000-candidate grid on 148 CTAs: 15.3 -> 13.5 ms; what remains is the double-double
+    // arithmetic itself -- n^3/6 multiply-subtracts of ~30 fp64 operations on ONE SM per candidate, ~3 ms each)
+    dd* colj = ws_stride ? reinterpret_cast<dd*>(toff + KMAX) : nullptr;  // [n + 2]
     const bool tabbed = (mode == 0) && a.dtab != nullptr && tab_rowmajor;  // layout 0 (row-major) or 2 (tile64)
     const size_t tper = (a.tab_layout == 2) ? regs_table_doubles(a.npad) : (size_t)a.npad * a.npad;
     const int n = a.n, k = a.k, m = n + 2;
@@ -138,9 +143,40 @@ __global__ void __launch_bounds__(THREADS) krig_rescue_kernel(const NllArgs a, c
             }
             if (threadIdx.x == 0) logdet = dd_add_d(logdet, log(d.hi) + d.lo / d.hi);
             const dd linv = dd_recip(dd_sqrt(d));
-            for (int i = j + 1 + threadIdx.x; i < m; i += THREADS) A[tri(i, j)] = dd_mul(A[tri(i, j)], linv);
+            for (int i = j + 1 + threadIdx.x; i < m; i += THREADS) {
+                const dd v = dd_mul(A[tri(i, j)], linv);
+                A[tri(i, j)] = v;
+                if (colj != nullptr) colj[i] = v;
+            }
             __syncthreads();
             const int rem = m - j - 1;  // trailing rows j+1 .. m-1; their lower triangle, flat over all threads
+            if (colj != nullptr) {  // block-uniform; same arithmetic per element as the loop below
+                const int tot = rem * (rem + 1) / 2;
+                for (int t0 = threadIdx.x; t0 < tot; t0 += 4 * THREADS) {
+                    dd v[4];
+                    size_t idx[4];
+                    int ri[4], ci[4];
+                    bool act[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int t = t0 + u * THREADS;
+                        act[u] = t < tot;
+                        if (act[u]) {
+                            int r, c;
+                            tri_rc(t, r, c);
+                            ri[u] = j + 1 + r;
+                            ci[u] = j + 1 + c;
+                            act[u] = ci[u] < n;
+                            idx[u] = tri(ri[u], ci[u]);
+                            if (act[u]) v[u] = A[idx[u]];
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (act[u]) A[idx[u]] = dd_fnma(colj[ri[u]], colj[ci[u]], v[u]);
+                }
+                continue;
+            }
             for (int t = threadIdx.x; t < rem * (rem + 1) / 2; t += THREADS) {
                 int r, c;
                 tri_rc(t, r, c);
@@ -265,7 +301,7 @@ cudaError_t launch_rescue(const NllArgs& a, int mode, cudaStream_t st, long long
             if (grid > a.C) grid = a.C;
             e = cudaMallocAsync((void**)&ws, (size_t)grid * mat, st);
             if (e == cudaSuccess) {
-                krig_rescue_kernel<1024><<<(int)grid, 1024, fixed, st>>>(a, mode, list, cnt, ws, rescue_elems(a.n), fo, rowmajor);
+                krig_rescue_kernel<1024><<<(int)grid, 1024, fixed + (size_t)(a.n + 2) * sizeof(dd), st>>>(a, mode, list, cnt, ws, rescue_elems(a.n), fo, rowmajor);
                 e = cudaGetLastError();
             }
         }
