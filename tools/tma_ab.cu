@@ -4,7 +4,8 @@
 //   variant 1: cp.async.bulk (TMA bulk copy, UBLKCP), 512 bytes per instruction issued by ONE lane, completion through an
 //              mbarrier with expect_tx, consumer waits with mbarrier.try_wait.parity
 // Same ring depth, same DMMA consumer, same global layout (a private workspace per CTA, walked tile by tile and re-walked).
-// Build:  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tma_ab tools/tma_ab.cu
+// Build:  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -cudart shared -o tools/tma_ab_bin tools/tma_ab.cu   (shared runtime: a
+//         statically linked one embeds the names of every runtime entry point in the binary; delete the binary after the run)
 // Run:    ./tma_ab <workspace KB per CTA, a power of two> <k-steps per warp> [warps per CTA <= 4] [CTAs per SM = 4]
 #include <cuda_runtime.h>
 
