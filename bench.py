@@ -55,9 +55,9 @@ def flops_like(n, k):
 
 def measured_traffic():
     """DRAM bytes of the dominant kernel per launch, from one `ncu --set full` capture of the same launch
-    (profiles/r01_nll_small_traffic.json); None if the record is absent"""
+    (profiles/r02_nll_regs_traffic.json); None if the record is absent"""
     try:
-        with open(os.path.join(ROOT, 'profiles', 'r01_nll_small_traffic.json')) as f:
+        with open(os.path.join(ROOT, 'profiles', 'r02_nll_regs_traffic.json')) as f:
             return json.load(f)['traffic_bytes_per_launch']
     except Exception:
         return None
@@ -358,7 +358,7 @@ def run_gpu(args):
     achieved = fl / (kernel_ms * 1e-3) / 1e12
     roofline = {
         'bound': 'tensor', 'bound_detail': 'fp64 pipe (DMMA / DFMA share one 37 TFLOP/s peak); not HBM',
-        'kernel': 'krig_nll_small_kernel<8,2,2>', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
+        'kernel': 'krig_nll_regs_kernel<8,2,2,4,3>', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
         'frac': achieved / peak_tf, 'peak_source': peak_src, 'traffic': measured_traffic() if world == 1 else None,
         'traffic_unit': 'bytes of DRAM traffic per launch (ncu); algorithmic bytes = 8 per candidate + tables once',
         'flops_per_eval': flops_like(N_SAMPLES, K_DIM),
@@ -450,14 +450,14 @@ def run_gpu(args):
                  'unit': 'predictions/s', 'queries_per_gpu': nq5, 'ms': pred_ms,
                  'value_note': 'arbitrary query points (sm_krig_predict); mesh_path = the same mesh through sm_krig_predict_mesh',
                  'mesh_path': {'value': world * nq5 / (mesh_ms * 1e-3), 'unit': 'predictions/s', 'ms': mesh_ms,
-                               'kernel': 'krig_predict_mse_kernel<8,2,2,MESH>', 'flops_per_query': f_mesh,
+                               'kernel': 'krig_predict_mse_kernel<5,3,2,1> (mesh)', 'flops_per_query': f_mesh,
                                'frac': f_mesh * nq5 / (mesh_ms * 1e-3) / P_FMA,
                                'hbm_gbs_achieved': nq5 * 16 / (mesh_ms * 1e-3) / 1e9,
                                'mean_only_predictions_per_s': world * nq5 / (mesh_mean_ms * 1e-3),
                                'mean_only_hbm_gbs_achieved': nq5 * 8 / (mesh_mean_ms * 1e-3) / 1e9},
                  'mean_only_predictions_per_s': world * nq5 / (pred_mean_ms * 1e-3),
                  'roofline': {'bound': 'tensor', 'bound_detail': 'fp64 pipe: n^2 DMMA contraction + n exp + n k pow per query; not HBM '
-                                                                 '(32 B per query)', 'kernel': 'krig_predict_mse_kernel<8,2,2>',
+                                                                 '(32 B per query)', 'kernel': 'krig_predict_mse_kernel<6,2,2,0>',
                               'flops_per_query': f_mse, 'exp_per_query': n5, 'pow_per_query': 2 * n5,
                               'achieved': f_mse * nq5 / (pred_ms * 1e-3) / 1e12, 'peak': peak_tf, 'unit': 'TFLOP/s',
                               'frac': f_mse * nq5 / (pred_ms * 1e-3) / P_FMA, 'frac_pipe_time_bound': t_pipe / (pred_ms * 1e-3),
