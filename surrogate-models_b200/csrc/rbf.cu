@@ -9,6 +9,8 @@
 // partial pivoting (what np.linalg.solve does), as does a gaussian matrix that is not numerically SPD.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "fastmath.cuh"
 #include "fastmath2.cuh"
 #include "tile_chol.cuh"
@@ -365,6 +367,139 @@ __global__ void __launch_bounds__(1024) lu_panel_kernel(double* __restrict__ A, 
     }
 }
 
+// The same panel factorisation spread over a cooperative grid.  On one CTA the panel is rewritten through that SM's L2 port once
+// per column (1 MB per column step at n = 4096: 0.54 ms per panel, 69 of the 83 ms of an `mq` solve -- ncu launch list).  Here
+// every CTA keeps a slab of <= 32 panel rows in shared memory for the whole panel.  Per column: every CTA publishes its largest
+// entry of the column WITH that row's panel values, the CTA holding the row at the pivot position publishes that row, ONE grid
+// barrier, then every CTA finds the same winner (largest magnitude, lowest row on a tie, as idamax), swaps its own rows from
+// the published copies and eliminates locally.  The published arrays are double-buffered by column parity (a CTA writes
+// column j + 2 only after barrier j + 1, which every CTA reaches after it has read column j).  Same arithmetic per element
+// as lu_panel_kernel (reciprocal of the pivot, one fma per update); the right-hand side rides along.
+constexpr int LUC_SMAX = 32, LUC_GMAX = 160, LUC_P = LU_NB + 1;
+struct LuCoopScratch {
+    double val[2][LUC_GMAX];
+    int row[2][LUC_GMAX];
+    double rowvals[2][LUC_GMAX][LUC_P];  // [..][LU_NB]: the right-hand side of that row
+    double qrow[2][LUC_P];               // the row at the pivot position before the swap
+};
+
+__global__ void __launch_bounds__(256) lu_panel_coop_kernel(double* __restrict__ A, double* __restrict__ rhs, int n, int c0, int nbw,
+                                                            int* __restrict__ piv, int* __restrict__ info, LuCoopScratch* __restrict__ sc,
+                                                            int S) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double Ps[LUC_SMAX * LUC_P];  // [row of the slab][panel column], pitch 33
+    __shared__ double rs[LUC_SMAX];
+    __shared__ double prow[LUC_P];
+    __shared__ double red_v[8];
+    __shared__ int red_i[8], red_b[8], win_s[2];
+    const int G = gridDim.x, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int r0 = c0 + b * S, r1 = min(r0 + S, n), ns = max(r1 - r0, 0);
+    for (int t = tid; t < ns * nbw; t += blockDim.x) {
+        const int i = t % ns, jj = t / ns;
+        Ps[i * LUC_P + jj] = A[(size_t)(c0 + jj) * n + r0 + i];
+    }
+    for (int i = tid; i < ns; i += blockDim.x) rs[i] = rhs[r0 + i];
+    __syncthreads();
+    for (int j = 0; j < nbw; ++j) {
+        const int c = c0 + j, buf = j & 1;
+        if (wid == 0) {  // this CTA's candidate: rows at positions >= c
+            double v = -1.0;
+            int ri = n;
+            if (lane < ns && r0 + lane >= c) {
+                v = fabs(Ps[lane * LUC_P + j]);
+                ri = r0 + lane;
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, ri, o);
+                if (ov > v || (ov == v && oi < ri)) { v = ov; ri = oi; }
+            }
+            if (lane == 0) {
+                sc->val[buf][b] = v;
+                sc->row[buf][b] = ri;
+            }
+            if (v >= 0.0) {
+                if (lane < nbw) sc->rowvals[buf][b][lane] = Ps[(ri - r0) * LUC_P + lane];
+                if (lane == 0) sc->rowvals[buf][b][LU_NB] = rs[ri - r0];
+            }
+            if (c >= r0 && c < r1) {
+                if (lane < nbw) sc->qrow[buf][lane] = Ps[(c - r0) * LUC_P + lane];
+                if (lane == 0) sc->qrow[buf][LU_NB] = rs[c - r0];
+            }
+        }
+        __threadfence();
+        grid.sync();
+        {   // the global pivot, identically in every CTA
+            double v = -1.0;
+            int ri = n, bb = 0;
+            if (tid < G) {
+                v = __ldcg(&sc->val[buf][tid]);  // written by other CTAs before the barrier: read past L1
+                ri = __ldcg(&sc->row[buf][tid]);
+                bb = tid;
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, ri, o), ob = __shfl_xor_sync(0xffffffffu, bb, o);
+                if (ov > v || (ov == v && oi < ri)) { v = ov; ri = oi; bb = ob; }
+            }
+            if (lane == 0) { red_v[wid] = v; red_i[wid] = ri; red_b[wid] = bb; }
+            __syncthreads();
+            if (wid == 0) {
+                v = (lane < 8) ? red_v[lane] : -1.0;
+                ri = (lane < 8) ? red_i[lane] : n;
+                bb = (lane < 8) ? red_b[lane] : 0;
+                for (int o = 4; o > 0; o >>= 1) {
+                    const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, ri, o), ob = __shfl_xor_sync(0xffffffffu, bb, o);
+                    if (ov > v || (ov == v && oi < ri)) { v = ov; ri = oi; bb = ob; }
+                }
+                if (lane == 0) {
+                    win_s[0] = ri;
+                    win_s[1] = bb;
+                    if (b == 0) {
+                        piv[c] = ri;
+                        if (!(v > 0.0) && *info == 0) *info = c + 1;  // exactly singular (LAPACK info > 0)
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        const int p = win_s[0], wb = win_s[1];
+        if (tid < nbw) prow[tid] = __ldcg(&sc->rowvals[buf][wb][tid]);
+        if (tid == LU_NB) prow[LU_NB] = __ldcg(&sc->rowvals[buf][wb][LU_NB]);
+        __syncthreads();
+        if (p != c && p < n) {  // rows c and p trade places: each owner takes the published copy of the other row
+            if (p >= r0 && p < r1) {
+                if (tid < nbw) Ps[(p - r0) * LUC_P + tid] = __ldcg(&sc->qrow[buf][tid]);
+                if (tid == LU_NB) rs[p - r0] = __ldcg(&sc->qrow[buf][LU_NB]);
+            }
+            if (c >= r0 && c < r1) {
+                if (tid < nbw) Ps[(c - r0) * LUC_P + tid] = prow[tid];
+                if (tid == LU_NB) rs[c - r0] = prow[LU_NB];
+            }
+        }
+        __syncthreads();
+        const double d = 1.0 / prow[j], rc = prow[LU_NB];
+        if (tid < ns && r0 + tid > c) {
+            const double l = Ps[tid * LUC_P + j] * d;
+            Ps[tid * LUC_P + j] = l;
+            rs[tid] = fma(-l, rc, rs[tid]);
+        }
+        __syncthreads();
+        const int w = nbw - j - 1;
+        for (int t = tid; t < ns * w; t += blockDim.x) {
+            const int i = t % ns, jj = j + 1 + t / ns;
+            if (r0 + i > c) Ps[i * LUC_P + jj] = fma(-Ps[i * LUC_P + j], prow[jj], Ps[i * LUC_P + jj]);
+        }
+        __syncthreads();
+    }
+    for (int t = tid; t < ns * nbw; t += blockDim.x) {
+        const int i = t % ns, jj = t / ns;
+        A[(size_t)(c0 + jj) * n + r0 + i] = Ps[i * LUC_P + jj];
+    }
+    for (int i = tid; i < ns; i += blockDim.x) rhs[r0 + i] = rs[i];
+}
+
 // columns right of the panel: the panel's row swaps, then U12 = L11^-1 A12 (unit lower L11, one column per thread)
 __global__ void __launch_bounds__(256) lu_swap_trsm_kernel(double* __restrict__ A, int n, int c0, int nbw, const int* __restrict__ piv) {
     __shared__ double L11[LU_NB * LU_NB];
@@ -506,9 +641,26 @@ cudaError_t launch_rbf_fit(const double* X, const double* y, int n, int k, int k
         int* piv = nullptr;
         e = cudaMallocAsync((void**)&piv, (size_t)n * sizeof(int), st);
         if (e != cudaSuccess) return e;
+        static const bool coop_off = [] { const char* v = getenv("SMB_LU_COOP_OFF"); return v && v[0] == '1'; }();
+        LuCoopScratch* sc = nullptr;
+        if (cudaMallocAsync((void**)&sc, sizeof(LuCoopScratch), st) != cudaSuccess) sc = nullptr;
         for (int c0 = 0; c0 < n; c0 += LU_NB) {
             const int nbw = n - c0 < LU_NB ? n - c0 : LU_NB;
-            lu_panel_kernel<<<1, n - c0 > 512 ? 1024 : 256, 0, st>>>(A, coeff, n, c0, nbw, piv, info);
+            const int R = n - c0;
+            int G = sm_count() < LUC_GMAX ? sm_count() : LUC_GMAX;
+            const int S = (R + G - 1) / G;
+            bool coop = !coop_off && sc != nullptr && R >= 768 && S <= LUC_SMAX;
+            if (coop) {  // panel rows spread over the SMs (one grid barrier per column); few rows: one CTA is faster
+                G = (R + S - 1) / S;
+                double* Aarg = A;
+                double* rarg = coeff;
+                int narg = n, carg = c0, warg = nbw, Sarg = S;
+                void* args[] = {&Aarg, &rarg, &narg, &carg, &warg, &piv, &info, &sc, &Sarg};
+                e = cudaLaunchCooperativeKernel((const void*)lu_panel_coop_kernel, dim3(G), dim3(256), args, 0, st);
+                if (e != cudaSuccess) return e;
+            } else {
+                lu_panel_kernel<<<1, n - c0 > 512 ? 1024 : 256, 0, st>>>(A, coeff, n, c0, nbw, piv, info);
+            }
             const int rest = n - c0 - nbw;
             if (rest > 0) {
                 lu_swap_trsm_kernel<<<(rest + 255) / 256, 256, 0, st>>>(A, n, c0, nbw, piv);
@@ -517,6 +669,7 @@ cudaError_t launch_rbf_fit(const double* X, const double* y, int n, int k, int k
             if (launches) *launches += rest > 0 ? 3 : 1;
         }
         cudaFreeAsync(piv, st);
+        if (sc) cudaFreeAsync(sc, st);
     } else {
         for (int c = 0; c < n; ++c) {
             lu_pivot_kernel<<<1, 256, 0, st>>>(A, coeff, n, c, info);
