@@ -562,12 +562,19 @@ def run_gpu(args):
     r4.update_param(1.0, 'gaus')
     torch.cuda.synchronize()
     fit_s = time.perf_counter() - t0
+    r4m = RBF(X4, y4)                                            # non-definite kernel: blocked LU with cooperative panel factorisation
+    r4m.update_param(0.5, 'mq')
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    r4m.update_param(0.5, 'mq')
+    torch.cuda.synchronize()
+    fit_mq_s = time.perf_counter() - t0
     nq4 = 2000000
     xq4 = device.to_dev(workloads.c4_queries(nq4, seed=1 + rank))
     c4_ms = timed_ms(lambda: r4.predict_device(xq4))
     f_rbf = 4096 * (3 * 3 + 2)                                   # n (3k + 2) flop + n exp per query
     secondary_c4 = {'metric': 'rbf evaluations/s (gaus, n=4096, k=3)', 'value': world * nq4 / (c4_ms * 1e-3), 'unit': 'predictions/s',
-                    'queries_per_gpu': nq4, 'ms': c4_ms, 'weight_solve_s': fit_s,
+                    'queries_per_gpu': nq4, 'ms': c4_ms, 'weight_solve_s': fit_s, 'weight_solve_mq_s': fit_mq_s,
                     'kernel_evals_per_s': world * nq4 * 4096 / (c4_ms * 1e-3),
                     'roofline': {'bound': 'tensor', 'bound_detail': 'fp64 pipe: 11 flop + 1 exp per (query, sample) pair; not HBM',
                                  'kernel': 'rbf_predict_kernel<3>', 'flops_per_query': f_rbf, 'exp_per_query': 4096,
