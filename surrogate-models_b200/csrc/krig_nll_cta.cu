@@ -28,6 +28,7 @@
 // Reference semantics: mylibs/kriging.py:53-116,130-141 per candidate; enumeration of mylibs/likeli_optimizer.py:50-97.
 #include <cstdlib>
 
+#include "cta_slots.h"
 #include "nll_small_common.cuh"
 
 namespace smb {
@@ -55,15 +56,6 @@ extern "C" int smb_cta_phase_read(unsigned long long* out, int reset) {
 #define CPH_MARK(slot)
 #endif
 
-__host__ __device__ inline int cta_band_slots(int NT, int band) {
-    const int x = band + 2, y = NT - 1 - band;
-    return x < y ? x : y;
-}
-__host__ __device__ inline int cta_slots(int NT) {
-    int s = 0;
-    for (int b = 0; b + 1 < NT; ++b) s += cta_band_slots(NT, b);
-    return s > 0 ? s : 1;
-}
 // doubles ahead of the tile slots: exp table | y | rhs rows | W[2] | diagonal working tile | red[16] | ctl | offset table
 __host__ __device__ constexpr int cta_fixed_doubles(int ntm) {
     return EXP_TAB + 8 * ntm + 16 * ntm + 128 + 64 + 16 + 2 + (ntm * ntm * 2 + 15) / 16 * 2;
@@ -124,12 +116,7 @@ __global__ void __launch_bounds__(32 * WARPS, MINB) krig_nll_cta_kernel(const Nl
     for (int j = threadIdx.x; j < 8 * NTM; j += blockDim.x) y_s[j] = (j < a.n) ? a.y[j] : 0.0;
     for (int t = threadIdx.x; t < NT * NT; t += blockDim.x) {
         const int I = t / NT, K = t - I * NT;
-        if (K < I) {
-            const int band = I - K - 1;
-            int base = 0;
-            for (int b = 0; b < band; ++b) base += cta_band_slots(NT, b);
-            toff[I * NTM + K] = (unsigned short)((base + K % cta_band_slots(NT, band)) * 64);
-        }
+        if (K < I) toff[I * NTM + K] = (unsigned short)(cta_slot_of(NT, I, K) * 64);
     }
     if (threadIdx.x == 0) ctl[0] = 0;
     __syncthreads();

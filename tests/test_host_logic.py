@@ -215,3 +215,21 @@ def test_odometer_and_timer_semantics():
     t.tic()
     lap = t.toc()
     assert 0 <= lap < 0.01 and t.get_time() >= lap
+
+
+def test_cta_kernel_slot_packing_replay(tmp_path):
+    """csrc/cta_slots.h (live-range packing of the factor tiles in krig_nll_cta.cu) compiled for the host: a replay of the kernel's
+    read / store schedule (tools/cta_slots_check.cpp) never finds a tile overwritten before its last read, for every tile count the
+    kernel accepts and beyond; the slot count is NT^2/4 + O(NT) (71 at n = 128, 271 at n = 256)"""
+    import ctypes
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = str(tmp_path / 'libcta_slots.so')
+    subprocess.run(['g++', '-O2', '-shared', '-fPIC', os.path.join(root, 'tools', 'cta_slots_check.cpp'), '-o', so], check=True)
+    lib = ctypes.CDLL(so)
+    out = (ctypes.c_int * 40)()
+    assert lib.cta_slots_check(2, 41, out) == 0
+    slots = dict(zip(range(2, 42), out))
+    assert slots[16] == 71 and slots[32] == 271 and slots[22] == 131
+    for nt in range(4, 42):
+        assert slots[nt] <= nt * nt // 4 + nt and slots[nt] < nt * (nt - 1) // 2 + 1
